@@ -1,0 +1,200 @@
+/* rlvi_b200.h -- C ABI of librlvi_b200.so: the RLVI E-step + weighted M-step hot path on B200 (sm_100a).
+ *
+ * The reference (akarakulev/rlvi) is pure Python; it has no FFI.  Its "plugin API" for this path is
+ * the set of Python function signatures in standard-learning/rlvi.py, standard-learning/utils.py,
+ * deep-learning/methods/train_rlvi.py and online-learning/main.py.  Each entry
+ * point below names the reference expression it replaces; the Python drop-in modules in rlvi_b200/
+ * (rlvi.py, utils.py, deep.py, online.py) keep the reference signatures and call ONLY these symbols
+ * through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain C types only; every array pointer is a DEVICE pointer owned by the caller unless the
+ *    parameter name ends in `_host`; matrices are row-major, C-contiguous: X[n][d];
+ *  - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream); nothing here synchronises the device except rlvi_ctx_* and the
+ *    `*_host` convenience calls, which say so;
+ *  - scratch memory lives in the context (rlvi_ctx): it grows on demand (a cudaMalloc, the only place
+ *    an allocation can happen) and is reused, so steady-state calls never allocate;
+ *  - return value: 0 = RLVI_OK, < 0 = error; rlvi_last_error() gives the thread-local message;
+ *  - reductions are deterministic (fixed-order two-stage trees, no floating-point atomics): the same
+ *    inputs on the same GPU model give the same bits on every run.
+ */
+#ifndef RLVI_B200_H
+#define RLVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLVI_OK 0
+#define RLVI_ERR_INVALID (-1)     /* bad argument (null pointer, n < 0, ...)            */
+#define RLVI_ERR_CUDA (-2)        /* a CUDA runtime call failed; see rlvi_last_error()  */
+#define RLVI_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover (e.g. d > 1024) */
+#define RLVI_ERR_NOMEM (-4)       /* scratch allocation failed                          */
+
+typedef struct rlvi_ctx rlvi_ctx;
+
+/* ---- library / context --------------------------------------------------------------------- */
+int rlvi_version(void);                      /* 100 * major + minor                               */
+const char* rlvi_last_error(void);           /* thread-local, never NULL                          */
+int rlvi_ctx_create(int device, rlvi_ctx** out);   /* binds to `device`; synchronous              */
+int rlvi_ctx_destroy(rlvi_ctx* ctx);               /* frees the scratch; synchronous              */
+int rlvi_ctx_sm_count(const rlvi_ctx* ctx);        /* SMs of the bound device (148 on B200)       */
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+int64_t rlvi_ctx_launch_count(const rlvi_ctx* ctx);
+
+/* ---- E-step: epsilon fixed point ------------------------------------------------------------ */
+/* Which reference loop the iteration reproduces. */
+enum rlvi_fp_variant {
+  /* standard-learning/rlvi.py:8-20  update_weights: pi0 = 0.95; eps = 1 - mean(pi);
+   * rho = eps/(1-eps); pi' = e/(rho+e); stop when ||pi'-pi||_2 < tol; returns the last pi'.      */
+  RLVI_FP_STANDARD = 0,
+  /* online-learning/main.py:45-58  update_weights_rlvi: pi0 = 0.5; rho = avg/(1-avg);
+   * pi' = rho e/(1+rho e); same stop; result divided by max(pi') * n.                            */
+  RLVI_FP_ONLINE = 1,
+  /* deep-learning/methods/train_rlvi.py:14-38  update_sample_weights: residuals -= min (in place);
+   * avg0 = 0.95; pi' = rho e/(1+rho e); first-pass error against the INCOMING weights;
+   * weights overwritten; finally weights /= max(weights).                                        */
+  RLVI_FP_DEEP = 2
+};
+
+/* Written by the fixed-point kernels into device memory (40 bytes); copy it back when needed. */
+typedef struct rlvi_fp_result {
+  double eps;     /* STANDARD: the last eps = 1 - mean(pi) used; ONLINE/DEEP: 1 - last avg used    */
+  double rho;     /* the last ratio used                                                           */
+  double sum_pi;  /* sum of the returned posteriors BEFORE the variant's normalisation             */
+  double err;     /* ||pi' - pi||_2 of the last pass                                               */
+  int32_t iters;  /* passes executed (1..maxiter)                                                  */
+  int32_t converged; /* 1 if err < tol stopped the loop, 0 if maxiter did                          */
+} rlvi_fp_result;
+
+/* Optional multi-GPU exchange for the fixed point (one process per GPU; the sample dimension is
+ * sharded).  `inbox` is THIS rank's window of rlvi_fp_dist_inbox_doubles(world)
+ * doubles, zeroed once at setup; `peer_inbox` is a DEVICE array of `world` pointers, entry r addressing rank r's
+ * window through NVLink peer mapping (entry `rank` == inbox).  Every pass each rank stores its three
+ * partial reductions + a sequence tag into slot `rank` of every peer's window, then sums the `world`
+ * slots of its own window in rank order, so all ranks obtain the same bits and take the same stop
+ * decision.  NULL => single GPU. */
+typedef struct rlvi_fp_dist {
+  int32_t rank;
+  int32_t world;
+  int64_t n_global;          /* total samples over all ranks (the mean's denominator)             */
+  double* inbox;             /* device                                                            */
+  double* const* peer_inbox; /* device array [world] of device pointers                           */
+  uint64_t call_index;       /* 1, 2, 3, ...: the same on every rank, +1 per fixed-point call     */
+} rlvi_fp_dist;
+int rlvi_fp_dist_inbox_doubles(int world);   /* size of one rank's window, in doubles             */
+
+/* FP64 fixed point (STANDARD or ONLINE).
+ *   losses   [n]  per-sample loss l_i, or NULL when `e_work` already holds e_i = exp(-l_i)
+ *   scale    device scalar s or NULL (=1): the kernel uses e_i = exp(-s * l_i); lets the caller fold
+ *            the `0.5 / sigma2` of rlvi.py:51,59,74,83 in without a host round trip
+ *   e_work   [n]  scratch the kernel fills with e_i on its first pass and re-reads afterwards
+ *   pi_out   [n]  the returned posteriors (may alias `losses`; may NOT alias `e_work`)
+ *   result   device rlvi_fp_result                                                               */
+int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                         double* e_work, int64_t n, double tol, int maxiter, double* pi_out,
+                         rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
+
+/* FP32 fixed point, DEEP variant: `residuals` [n] and `weights` [n] are both updated in place,
+ * exactly as methods/train_rlvi.py:14-38 leaves them.  `e_work` [n] is FP32 scratch. */
+int rlvi_fixed_point_deep_f32(rlvi_ctx* ctx, float* residuals, float* weights, float* e_work, int64_t n,
+                              float tol, int maxiter, rlvi_fp_result* result, const rlvi_fp_dist* dist,
+                              void* stream);
+
+/* standard-learning/rlvi.py:34-39  shift_obj's inner sum:  out[0] = sum_i t_i/(c + t_i),
+ * t_i = exp(-l_i + s).  One pass; the Brent search (scipy) stays on the host.
+ * If `pi_out` != NULL the per-sample ratios are also written (rlvi.py:42). */
+int rlvi_shift_sum_f64(rlvi_ctx* ctx, const double* losses, int64_t n, double shift, double c,
+                       double* pi_out, double* out_sum, void* stream);
+
+/* ---- per-sample losses (one pass over X) ------------------------------------------------------ */
+enum rlvi_loss_kind {
+  /* utils.py:19-21 cross_entropy: phi = b + x.theta;  l = -y phi + phi + log1p(exp(-phi)).
+   * params = [b, theta(d)] if `intercept` else [theta(d)].                                        */
+  RLVI_LOSS_LOGISTIC_CE = 0,
+  /* utils.py:62-64 the loss sklearn_log_reg reports: l = -log P(class 0|x) = log(1 + exp(phi)),
+   * label-independent (quirk Q3).  params as above.                                               */
+  RLVI_LOSS_SOFTPLUS = 1,
+  /* rlvi.py:72,81 squared residual: l = (y - x.theta)^2.   params = [theta(d)] (or [b, theta]).   */
+  RLVI_LOSS_SQRES = 2,
+  /* rlvi.py:49,57 squared distance to the mean: l = ||theta - x||^2.   params = [theta(d)].       */
+  RLVI_LOSS_SQDIST = 3,
+  /* utils.py:77-79 PCA reconstruction: l = ||x||^2 - (x.theta)^2.   params = [theta(d)].          */
+  RLVI_LOSS_PCA = 4,
+  /* utils.py:93-101 Gaussian NLL: l = 0.5 [(x-mu)^T P (x-mu) + c].
+   * params = [c, mu(d), P(d*d) row-major] with P = cov^-1, c = log|cov| + d log(2 pi).            */
+  RLVI_LOSS_GAUSSIAN = 5
+};
+
+/* One pass over X (and y):
+ *   losses_out [n] (or NULL)      l_i
+ *   e_out      [n] (or NULL)      exp(-l_i), for the fixed point
+ *   weights    [n] (or NULL)      pi_i; when given, wsum_out[0] = sum pi_i l_i, wsum_out[1] = sum pi_i
+ *                                 (the sigma2 = pi.r2 / sum pi of rlvi.py:50,58,73,82)
+ *   wsum_out   device double[2] (required iff weights != NULL)                                     */
+int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const double* X, const double* y, int64_t n,
+                  int d, const double* params, const double* weights, double* losses_out, double* e_out,
+                  double* wsum_out, void* stream);
+
+/* ---- weighted M-step statistics (one pass over X) --------------------------------------------- */
+/* With w_i = weights_i (power = 1) or weights_i^2 (power = 2: the Gram of the pi-scaled rows that
+ * utils.py:82-84 hands to PCA):
+ *   S0   = sum w_i                       out[0]
+ *   Swy  = sum w_i y_i                   out[1]            (0 if y == NULL)
+ *   S1   = X^T w                         out[2 .. 2+d)     (rlvi.py:48,56; utils.py:103)
+ *   Sy   = X^T (w*y)                     out[2+d .. 2+2d)  (zeros if y == NULL; rlvi.py:71,80)
+ *   G    = X^T diag(w) X  (symmetric)    out[2+2d .. 2+2d+d*d) row-major, both triangles filled
+ *                                        (rlvi.py:70-71,79-80; utils.py:36-38,105); skipped (left
+ *                                        untouched) when want_gram == 0
+ * For power = 2, S1 is still X^T weights (first power: the column mean PCA subtracts) while S0 and G
+ * use the square.  `out` is a device buffer of rlvi_moments_out_doubles(d) doubles.               */
+int rlvi_moments_out_doubles(int d);
+int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
+                              int64_t n, int d, int power, int want_gram, double* out, void* stream);
+
+/* utils.py:40-41  the MM/gradient step's data term:  out[0] = sum c_i, out[1..d] = X^T c with
+ * c_i = w_i (sigmoid(b + x_i.theta) - y_i);  params = [b, theta(d)].  `out` = device double[d+1]. */
+int rlvi_logistic_grad_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
+                           int64_t n, int d, const double* params, double* out, void* stream);
+
+/* ---- deep path (FP32) ------------------------------------------------------------------------- */
+/* methods/train_rlvi.py:89-94 fused with its autograd backward (line 96):
+ *   loss_i = CE(logits_i, label_i);  residuals[indexes_i] = loss_i (detached: quirk Q8);
+ *   out_loss[0] = mean_i loss_i * weights[indexes_i];
+ *   dlogits_i = (softmax(logits_i) - onehot(label_i)) * weights[indexes_i] / B   (NULL = forward only)
+ *   out_correct[0], [1] = number of rows whose label is in the top-1 / top-5 logits (NULL = skip;
+ *   replaces utils.py:65-79 `accuracy`, called at train_rlvi.py:85).
+ * logits [B][C] FP32 row-major; labels, indexes int64 [B]; residuals, weights FP32 [n_train].
+ * `indexes` may be NULL (identity, n_train >= B).                                                 */
+int rlvi_wce_fwd_bwd_f32(rlvi_ctx* ctx, const float* logits, const int64_t* labels, const int64_t* indexes,
+                         const float* weights, float* residuals, int64_t batch, int classes,
+                         int64_t n_train, float* per_sample_out, float* dlogits, float* out_loss,
+                         int32_t* out_correct, void* stream);
+
+/* methods/train_rlvi.py:41-49 false_negative_criterion + lines 102-103 truncation:
+ *   beta = alpha * sum(1-w); walk the weights in descending order accumulating (1-w) while the
+ *   running mass stays <= beta; the threshold is the last weight reached (the smallest weight if
+ *   none fits: quirk Q9).  out_threshold[0] = max(prev_threshold, that value) (line 102; pass
+ *   prev_threshold = 0 for the bare criterion); if `truncate` != 0, weights[w < threshold] = 0 in
+ *   place.  The running mass is accumulated in FP64.                               */
+int rlvi_fn_threshold_f32(rlvi_ctx* ctx, float* weights, int64_t n, float alpha, float prev_threshold,
+                          int truncate, float* out_threshold, void* stream);
+
+/* ---- host-buffer convenience (the drop-in's NumPy route; bench.py's `e2e`) ------------------- */
+/* One E+M step of the logistic model on HOST buffers (pinned or pageable): chunks of X/y are copied
+ * H2D on a copy stream while the loss kernel consumes the previous chunk; then the fixed point and
+ * the statistics pass run on the device-resident copy, and the results are copied back.
+ *   X_host [n][d], y_host [n], params_host [d+1] (intercept first)
+ *   pi_host [n] (or NULL), moments_host [rlvi_moments_out_doubles(d)], result_host
+ * Needs n*(d+4)*8 bytes of device memory, taken from (and kept by) the context.  Synchronous. */
+int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, const double* y_host, int64_t n, int d,
+                               const double* params_host, double tol, int maxiter, double* pi_host,
+                               double* moments_host, rlvi_fp_result* result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLVI_B200_H */

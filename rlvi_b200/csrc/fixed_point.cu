@@ -1,0 +1,650 @@
+// fixed_point.cu -- the epsilon fixed point of the E-step as ONE persistent cooperative kernel.
+//
+// Replaces the Python loops of
+//   standard-learning/rlvi.py:8-20        (update_weights,          RLVI_FP_STANDARD, FP64)
+//   online-learning/main.py:45-58         (update_weights_rlvi,     RLVI_FP_ONLINE,   FP64)
+//   deep-learning/methods/train_rlvi.py:14-38 (update_sample_weights, RLVI_FP_DEEP,   FP32)
+// which launch ~10 array operations (and, on the GPU path, one host sync) per pass.
+//
+// Design: the posterior of pass k is a function of (e_i, rho_k) only, so no pi array
+// is kept between passes.  Pass 1 reads the losses, writes e_i = exp(-s*l_i) once, and every later
+// pass streams ONLY e (8 B/sample FP64) while accumulating  S = sum pi'  and  E = sum (pi' - pi)^2
+// with pi recomputed from the previous rho.  The scalar recurrence (eps, rho, stop test) is evaluated
+// redundantly by every block from the same bits, in the reference's FP64 operation order, so the
+// loop exits on the device without a host round trip.  A final pass writes pi.
+//
+// Cross-block reduction is deterministic: block partials -> grid barrier -> every block sums the
+// partials in the same fixed order.  With `dist` set, block 0 then stores the rank's totals into
+// every peer's inbox over NVLink and all blocks sum the `world` slots of their own inbox in rank
+// order, so every rank sees identical totals (same stop decision everywhere).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kFpThreads = 256;
+constexpr int kFpUnroll = 4;            // independent 128-bit loads in flight per thread
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+enum ReduceOp { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
+
+template <typename T>
+struct FpParams {
+  const T* losses;        // STANDARD/ONLINE: losses or NULL; DEEP: unused (residuals is in/out)
+  const double* scale;    // device scalar or NULL
+  T* e;                   // scratch e_i
+  T* pi_out;              // STANDARD/ONLINE output; DEEP: weights (in/out)
+  T* residuals;           // DEEP only (in/out)
+  int64_t n;
+  int64_t n_global;
+  double tol;
+  int maxiter;
+  double* partials;       // [2][grid][4]
+  unsigned int* control;  // [0] barrier counter, [1] failure flag
+  rlvi_fp_result* result;
+  int rank, world;
+  double* inbox;
+  double* const* peer_inbox;
+  unsigned long long call_index;
+};
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct FpShared {
+  double warp_part[3 * (kFpThreads / 32)];
+  double total[3];
+  int failed;
+};
+
+// Grid-wide (and, with dist, cross-GPU) reduction of three values; v2 uses OP2.  On return all
+// threads of all blocks (of all ranks) hold the same totals.  `round` counts reduction rounds and is
+// advanced here.  Returns false if a wait timed out (a peer died / launch was not co-resident).
+template <typename T, int OP2>
+__device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, double& v1, double& v2,
+                                unsigned int& round) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kFpThreads / 32;
+  // ---- block stage: fixed xor tree per warp, then warp partials in warp order
+  v0 = warp_sum(v0);
+  v1 = warp_sum(v1);
+  v2 = (OP2 == OP_SUM) ? warp_sum(v2) : (OP2 == OP_MIN ? warp_min(v2) : warp_max(v2));
+  __syncthreads();
+  if (lane == 0) {
+    sh.warp_part[warp] = v0;
+    sh.warp_part[NW + warp] = v1;
+    sh.warp_part[2 * NW + warp] = v2;
+  }
+  __syncthreads();
+  const unsigned int buf = round & 1u;
+  double* mine = p.partials + (size_t(buf) * gridDim.x + blockIdx.x) * 4;
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = sh.warp_part[2 * NW];
+    for (int w = 0; w < NW; ++w) {
+      a += sh.warp_part[w];
+      b += sh.warp_part[NW + w];
+      const double t = sh.warp_part[2 * NW + w];
+      c = (OP2 == OP_SUM) ? (w == 0 ? t : c + t) : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
+    }
+    mine[0] = a;
+    mine[1] = b;
+    mine[2] = c;
+    // ---- grid barrier (cooperative launch guarantees co-residency)
+    __threadfence();
+    atomicAdd(p.control, 1u);
+    const unsigned int target = (round + 1u) * gridDim.x;
+    const unsigned long long t0 = gtime_ns();
+    int failed = 0;
+    while (ld_acquire_u32(p.control) < target) {
+      if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
+      if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+    }
+    __threadfence();
+    sh.failed = failed;
+  }
+  __syncthreads();
+  if (sh.failed) return false;
+  // ---- every block sums all block partials in the same order (lane-strided, then xor tree)
+  if (warp == 0) {
+    const double* all = p.partials + size_t(buf) * gridDim.x * 4;
+    double a = 0.0, b = 0.0;
+    double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
+    for (unsigned int j = lane; j < gridDim.x; j += 32) {
+      a += ld_volatile_f64(all + j * 4 + 0);
+      b += ld_volatile_f64(all + j * 4 + 1);
+      const double t = ld_volatile_f64(all + j * 4 + 2);
+      c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = (OP2 == OP_SUM) ? warp_sum(c) : (OP2 == OP_MIN ? warp_min(c) : warp_max(c));
+    int failed = 0;
+    if (p.world > 1) {
+      // ---- cross-GPU stage: publish this rank's totals, then sum all ranks' in rank order
+      // Tag and window slot: two windows per call parity, so a fast rank that already started the
+      // NEXT call can never overwrite a slot a slow rank has not read yet (a rank can be at most one
+      // published round ahead of any peer).
+      const unsigned long long tag = (p.call_index << 20) + round + 1ull;
+      const size_t slot = (size_t(((p.call_index & 1ull) << 1) | buf) * p.world) * 4;
+      if (blockIdx.x == 0 && lane < p.world) {
+        double* dst = p.peer_inbox[lane] + slot + size_t(p.rank) * 4;
+        dst[0] = a;
+        dst[1] = b;
+        dst[2] = c;
+        __threadfence_system();
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
+      }
+      double ra = 0.0, rb = 0.0, rc = 0.0;
+      if (lane < p.world) {
+        const double* src = p.inbox + slot + size_t(lane) * 4;
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != tag) {
+          if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
+          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+        }
+        ra = ld_volatile_f64(src + 0);
+        rb = ld_volatile_f64(src + 1);
+        rc = ld_volatile_f64(src + 2);
+      }
+      failed = __any_sync(0xffffffffu, failed);
+      // rank-ordered sequential sum (world <= 32), identical on every rank
+      a = 0.0;
+      b = 0.0;
+      c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
+      for (int r = 0; r < p.world; ++r) {
+        a += __shfl_sync(0xffffffffu, ra, r);
+        b += __shfl_sync(0xffffffffu, rb, r);
+        const double t = __shfl_sync(0xffffffffu, rc, r);
+        c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
+      }
+    }
+    if (lane == 0) {
+      sh.total[0] = a;
+      sh.total[1] = b;
+      sh.total[2] = c;
+      sh.failed = failed;
+    }
+  }
+  __syncthreads();
+  v0 = sh.total[0];
+  v1 = sh.total[1];
+  v2 = sh.total[2];
+  round += 1u;
+  return sh.failed == 0;
+}
+
+// ---- vector access helpers ---------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<double> {
+  static constexpr int W = 2;
+  typedef double2 type;
+  __device__ static void load(const double* p, double (&o)[2]) { double2 v = *reinterpret_cast<const double2*>(p); o[0] = v.x; o[1] = v.y; }
+  __device__ static void store(double* p, const double (&o)[2]) { *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]); }
+};
+template <> struct Vec<float> {
+  static constexpr int W = 4;
+  typedef float4 type;
+  __device__ static void load(const float* p, float (&o)[4]) { float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  __device__ static void store(float* p, const float (&o)[4]) { *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]); }
+};
+
+// Load / store one chunk of W = (VEC ? Vec<T>::W : 1) consecutive elements starting at i; elements
+// at or past n read as `fill` and are not written.
+template <typename T, bool VEC, int W>
+__device__ __forceinline__ void load_chunk(const T* p, int64_t i, int64_t n, T (&o)[W], T fill) {
+  if constexpr (VEC) {
+    if (i + W <= n) {
+      Vec<T>::load(p + i, o);
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) o[j] = (i + j < n) ? p[i + j] : fill;
+}
+template <typename T, bool VEC, int W>
+__device__ __forceinline__ void store_chunk(T* p, int64_t i, int64_t n, const T (&o)[W]) {
+  if constexpr (VEC) {
+    if (i + W <= n) {
+      Vec<T>::store(p + i, o);
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    if (i + j < n) p[i + j] = o[j];
+}
+
+// Apply F(index, nvalid, ptr-relative lambda) over [0, n) with a grid-stride loop of vector chunks.
+// VEC: all arrays are 16-byte aligned -> 128-bit accesses, kFpUnroll chunks per thread per trip.
+template <typename T, bool VEC, typename F>
+__device__ __forceinline__ void for_each_chunk(int64_t n, F&& f) {
+  constexpr int W = VEC ? Vec<T>::W : 1;
+  const int64_t nchunks = (n + W - 1) / W;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // unrolled main part: kFpUnroll independent chunks per trip
+  for (; c + (kFpUnroll - 1) * stride < nchunks; c += kFpUnroll * stride) {
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) f(c + u * stride, u);
+  }
+  for (; c < nchunks; c += stride) f(c, 0);
+}
+
+// posterior formulas ------------------------------------------------------------------------------
+// STANDARD: pi = e / (rho + e)            (rlvi.py:15)
+// ONLINE/DEEP: pi = rho e / (1 + rho e)   (online main.py:52, train_rlvi.py:31)
+template <int VARIANT>
+__device__ __forceinline__ double post_f64(double e, double rho) {
+  if (VARIANT == RLVI_FP_STANDARD) return e / (rho + e);
+  const double a = rho * e;
+  return a / (1.0 + a);
+}
+
+// pi' and (pi' - pi) with ONE division: t = 1/((rho'+e)(rho+e)).
+template <int VARIANT>
+__device__ __forceinline__ void post_pair_f64(double e, double rho_new, double rho_old, double& pnew, double& diff) {
+  if (VARIANT == RLVI_FP_STANDARD) {
+    const double a = rho_new + e, b = rho_old + e;
+    const double prod = a * b;
+    if (prod > 1e-280 && prod < 1e280) {
+      const double t = e / prod;
+      pnew = t * b;
+      diff = t * (rho_old - rho_new);
+    } else {   // rho = inf (eps == 1, quirk Q1), e = inf/0 extremes: the reference's two divisions
+      pnew = e / a;
+      diff = pnew - e / b;
+    }
+  } else {
+    const double a = rho_new * e, b = rho_old * e;
+    const double prod = (1.0 + a) * (1.0 + b);
+    if (prod < 1e280) {
+      const double t = 1.0 / prod;
+      pnew = a * (1.0 + b) * t;
+      diff = (a - b) * t;
+    } else {
+      pnew = a / (1.0 + a);
+      diff = pnew - b / (1.0 + b);
+    }
+  }
+}
+
+// =================================================================================================
+// FP64 kernel: STANDARD and ONLINE
+// =================================================================================================
+template <int VARIANT, bool VEC>
+__global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<double> p) {
+  __shared__ FpShared sh;
+  unsigned int round = 0;
+  const double n_glob = double(p.n_global);
+  const double pi0 = (VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5;
+  const double s = p.scale ? *p.scale : 1.0;
+  const bool have_losses = p.losses != nullptr;
+  const double* losses = p.losses;
+  double* e = p.e;
+  constexpr int W = VEC ? 2 : 1;
+
+  // rho for pass 1 from the constant initial posterior, in the reference's operation order
+  double rho_new, rho_old = 0.0, eps;
+  if (VARIANT == RLVI_FP_STANDARD) {
+    eps = 1.0 - pi0;
+    rho_new = eps / (1.0 - eps);
+  } else {
+    eps = 1.0 - pi0;
+    rho_new = pi0 / (1.0 - pi0);
+  }
+
+  double S = 0.0, E = 0.0, emax = 0.0, err = 0.0;
+  int k = 1, converged = 0;
+  bool ok = true;
+  for (;; ++k) {
+    double s1 = 0.0, s2 = 0.0, mx = 0.0;
+    if (k == 1) {
+      for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
+        const int64_t i = c * W;
+        double ev[W];
+        if (have_losses) {
+          double lv[W];
+          load_chunk<double, VEC, W>(losses, i, p.n, lv, 0.0);
+#pragma unroll
+          for (int j = 0; j < W; ++j) ev[j] = exp(-(s * lv[j]));
+          store_chunk<double, VEC, W>(e, i, p.n, ev);
+        } else {
+          load_chunk<double, VEC, W>(e, i, p.n, ev, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          if (i + j < p.n) {
+            const double pn = post_f64<VARIANT>(ev[j], rho_new);
+            const double d = pn - pi0;
+            s1 += pn;
+            s2 = fma(d, d, s2);
+            mx = fmax(mx, ev[j]);
+          }
+        }
+      });
+    } else {
+      for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
+        const int64_t i = c * W;
+        double ev[W];
+        load_chunk<double, VEC, W>(e, i, p.n, ev, 0.0);
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          if (i + j < p.n) {
+            double pn, d;
+            post_pair_f64<VARIANT>(ev[j], rho_new, rho_old, pn, d);
+            s1 += pn;
+            s2 = fma(d, d, s2);
+          }
+        }
+      });
+    }
+    if (k == 1) {
+      ok = grid_allreduce3<double, OP_MAX>(p, sh, s1, s2, mx, round);
+      emax = mx;
+    } else {
+      double z = 0.0;
+      ok = grid_allreduce3<double, OP_SUM>(p, sh, s1, s2, z, round);
+    }
+    if (!ok) break;
+    S = s1;
+    E = s2;
+    err = sqrt(E);
+    if (err < p.tol) { converged = 1; break; }   // rlvi.py:18 / online main.py:54
+    if (k >= p.maxiter) break;
+    // next pass's ratio from the mean of the posteriors just computed
+    rho_old = rho_new;
+    const double avg = S / n_glob;
+    if (VARIANT == RLVI_FP_STANDARD) {
+      eps = 1.0 - avg;                 // rlvi.py:13
+      rho_new = eps / (1.0 - eps);     // rlvi.py:14
+    } else {
+      eps = 1.0 - avg;
+      rho_new = avg / (1.0 - avg);     // online main.py:51
+    }
+  }
+
+  // final pass: write the last pi' with the reference's own expression (single correctly rounded
+  // division), then the variant's normalisation
+  double norm = 1.0;
+  if (VARIANT == RLVI_FP_ONLINE) norm = post_f64<VARIANT>(emax, rho_new) * n_glob;   // max(pi') * n
+  if (ok) {
+    double* out = p.pi_out;
+    for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
+      const int64_t i = c * W;
+      double ev[W], pv[W];
+      load_chunk<double, VEC, W>(e, i, p.n, ev, 0.0);
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        pv[j] = post_f64<VARIANT>(ev[j], rho_new);
+        if (VARIANT == RLVI_FP_ONLINE) pv[j] = pv[j] / norm;
+      }
+      store_chunk<double, VEC, W>(out, i, p.n, pv);
+    });
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    rlvi_fp_result r;
+    r.eps = eps;
+    r.rho = rho_new;
+    r.sum_pi = S;
+    r.err = err;
+    r.iters = ok ? k : -1;
+    r.converged = ok ? converged : -1;
+    *p.result = r;
+  }
+}
+
+// =================================================================================================
+// FP32 kernel: DEEP (train_rlvi.py:14-38).  Elementwise arithmetic in FP32 exactly as torch does it;
+// the two sums are accumulated in FP64 and rounded to FP32 where torch holds an FP32 scalar.
+// =================================================================================================
+__device__ __forceinline__ float post_f32(float e, float rho) {
+  const float a = rho * e;
+  return __fdiv_rn(a, 1.0f + a);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kFpThreads) fp_kernel_deep_f32(const FpParams<float> p) {
+  __shared__ FpShared sh;
+  unsigned int round = 0;
+  const double n_glob = double(p.n_global);
+  constexpr int W = VEC ? 4 : 1;
+  float* res = p.residuals;
+  float* wts = p.pi_out;
+  float* e = p.e;
+  bool ok = true;
+
+  // residuals.min()  (train_rlvi.py:26)
+  double mn = INFINITY, z0 = 0.0, z1 = 0.0;
+  for_each_chunk<float, VEC>(p.n, [&](int64_t c, int) {
+    const int64_t i = c * W;
+    float rv[W];
+    load_chunk<float, VEC, W>(res, i, p.n, rv, INFINITY);
+#pragma unroll
+    for (int j = 0; j < W; ++j) mn = fmin(mn, double(rv[j]));
+  });
+  ok = grid_allreduce3<float, OP_MIN>(p, sh, z0, z1, mn, round);
+  const float rmin = float(mn);
+
+  float rho_new = float(0.95 / (1.0 - 0.95));   // Python-float ratio, cast when it meets the FP32 tensor
+  float rho_old = 0.0f;
+  float avg = 0.95f;
+  double S = 0.0, err = 0.0, emax = 0.0;
+  int k = 1, converged = 0;
+  if (ok) {
+    for (;; ++k) {
+      double s1 = 0.0, s2 = 0.0, mx = 0.0;
+      if (k == 1) {
+        for_each_chunk<float, VEC>(p.n, [&](int64_t c, int) {
+          const int64_t i = c * W;
+          float rv[W], wv[W], ev[W];
+          load_chunk<float, VEC, W>(res, i, p.n, rv, 0.f);
+          load_chunk<float, VEC, W>(wts, i, p.n, wv, 0.f);
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            rv[j] = rv[j] - rmin;          // residuals.sub_(min)
+            ev[j] = expf(-rv[j]);          // torch.exp(-residuals)
+          }
+          store_chunk<float, VEC, W>(res, i, p.n, rv);
+          store_chunk<float, VEC, W>(e, i, p.n, ev);
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            if (i + j < p.n) {
+              const float pn = post_f32(ev[j], rho_new);
+              const float d = pn - wv[j];    // first pass: against the INCOMING weights (line 32)
+              s1 += double(pn);
+              s2 = fma(double(d), double(d), s2);
+              mx = fmax(mx, double(ev[j]));
+            }
+          }
+        });
+      } else {
+        for_each_chunk<float, VEC>(p.n, [&](int64_t c, int) {
+          const int64_t i = c * W;
+          float ev[W];
+          load_chunk<float, VEC, W>(e, i, p.n, ev, 0.f);
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            if (i + j < p.n) {
+              const float pn = post_f32(ev[j], rho_new);
+              const float po = post_f32(ev[j], rho_old);   // == what `weights` held after the last pass
+              const float d = pn - po;
+              s1 += double(pn);
+              s2 = fma(double(d), double(d), s2);
+            }
+          }
+        });
+      }
+      if (k == 1) {
+        ok = grid_allreduce3<float, OP_MAX>(p, sh, s1, s2, mx, round);
+        emax = mx;
+      } else {
+        double z = 0.0;
+        ok = grid_allreduce3<float, OP_SUM>(p, sh, s1, s2, z, round);
+      }
+      if (!ok) break;
+      S = s1;
+      err = double(float(sqrt(s2)));          // torch.norm returns an FP32 scalar
+      avg = float(S / n_glob);                // weights.mean() (line 34) -- computed BEFORE the test
+      rho_old = rho_new;
+      const float rho_next = __fdiv_rn(avg, 1.0f - avg);
+      if (float(err) < float(p.tol)) { converged = 1; break; }
+      if (k >= p.maxiter) break;
+      rho_new = rho_next;
+    }
+  }
+  // weights[:] = pi'; weights /= weights.max()   (lines 33, 37)
+  const float rho_fin = rho_old;   // the ratio the last executed pass used
+  if (ok) {
+    const float wmax = post_f32(float(emax), rho_fin);
+    for_each_chunk<float, VEC>(p.n, [&](int64_t c, int) {
+      const int64_t i = c * W;
+      float ev[W], pv[W];
+      load_chunk<float, VEC, W>(e, i, p.n, ev, 0.f);
+#pragma unroll
+      for (int j = 0; j < W; ++j) pv[j] = __fdiv_rn(post_f32(ev[j], rho_fin), wmax);
+      store_chunk<float, VEC, W>(wts, i, p.n, pv);
+    });
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    rlvi_fp_result r;
+    r.eps = 1.0 - double(avg);
+    r.rho = double(rho_fin);
+    r.sum_pi = S;
+    r.err = err;
+    r.iters = ok ? k : -1;
+    r.converged = ok ? converged : -1;
+    *p.result = r;
+  }
+}
+
+// ---- host launch -----------------------------------------------------------------------------
+template <typename T, typename K>
+int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStream_t stream) {
+  int per_sm = 0;
+  RLVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFpThreads, 0));
+  if (per_sm < 1) {
+    rlvi_set_error("fixed-point kernel does not fit on an SM");
+    return RLVI_ERR_CUDA;
+  }
+  if (per_sm > 4) per_sm = 4;
+  int64_t max_grid = int64_t(ctx->sm_count) * per_sm;
+  int64_t want = (n_chunks + int64_t(kFpThreads) * kFpUnroll - 1) / (int64_t(kFpThreads) * kFpUnroll);
+  int grid = int(want < 1 ? 1 : (want > max_grid ? max_grid : want));
+  void* scratch = nullptr;
+  const size_t ctrl = 4096;
+  int rc = rlvi_scratch(ctx, ctrl + size_t(2) * grid * 4 * sizeof(double), &scratch);
+  if (rc != RLVI_OK) return rc;
+  p.control = reinterpret_cast<unsigned int*>(scratch);
+  p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + ctrl);
+  RLVI_CUDA(cudaMemsetAsync(p.control, 0, 64, stream));
+  void* args[] = {&p};
+  RLVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kFpThreads), args,
+                                        0, stream));
+  RLVI_LAUNCH_CHECK(ctx);
+  return RLVI_OK;
+}
+
+template <typename T>
+int fill_dist(FpParams<T>& p, const rlvi_fp_dist* dist, int64_t n) {
+  p.rank = 0;
+  p.world = 1;
+  p.n_global = n;
+  p.inbox = nullptr;
+  p.peer_inbox = nullptr;
+  p.call_index = 0;
+  if (dist && dist->world > 1) {
+    RLVI_REQUIRE(dist->world <= 32 && dist->rank >= 0 && dist->rank < dist->world, "bad rank/world");
+    RLVI_REQUIRE(dist->inbox && dist->peer_inbox && dist->n_global >= n, "incomplete rlvi_fp_dist");
+    p.rank = dist->rank;
+    p.world = dist->world;
+    p.n_global = dist->n_global;
+    p.inbox = dist->inbox;
+    p.peer_inbox = dist->peer_inbox;
+    p.call_index = dist->call_index;
+  } else if (dist) {
+    p.n_global = dist->n_global > 0 ? dist->n_global : n;
+  }
+  return RLVI_OK;
+}
+
+}  // namespace
+
+extern "C" int rlvi_fp_dist_inbox_doubles(int world) { return 4 * world * 4; }
+
+extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                                    double* e_work, int64_t n, double tol, int maxiter, double* pi_out,
+                                    rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream) {
+  RLVI_REQUIRE(ctx && e_work && pi_out && result, "null pointer");
+  RLVI_REQUIRE(n > 0, "n must be positive");
+  RLVI_REQUIRE(maxiter >= 1, "maxiter must be >= 1");
+  RLVI_REQUIRE(variant == RLVI_FP_STANDARD || variant == RLVI_FP_ONLINE, "FP64 variants: STANDARD, ONLINE");
+  RLVI_REQUIRE(pi_out != e_work, "pi_out may not alias e_work");
+  RlviDeviceGuard guard(ctx->device);
+  FpParams<double> p;
+  memset(&p, 0, sizeof(p));
+  p.losses = losses;
+  p.scale = scale;
+  p.e = e_work;
+  p.pi_out = pi_out;
+  p.n = n;
+  p.tol = tol;
+  p.maxiter = maxiter;
+  p.result = result;
+  int rc = fill_dist(p, dist, n);
+  if (rc != RLVI_OK) return rc;
+  const bool vec = rlvi_aligned16(e_work) && rlvi_aligned16(pi_out) && (!losses || rlvi_aligned16(losses));
+  const int64_t chunks = vec ? (n + 1) / 2 : n;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (variant == RLVI_FP_STANDARD)
+    return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, true>, p, chunks, st)
+               : launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, false>, p, chunks, st);
+  return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_ONLINE, true>, p, chunks, st)
+             : launch_fp(ctx, fp_kernel_f64<RLVI_FP_ONLINE, false>, p, chunks, st);
+}
+
+extern "C" int rlvi_fixed_point_deep_f32(rlvi_ctx* ctx, float* residuals, float* weights, float* e_work,
+                                         int64_t n, float tol, int maxiter, rlvi_fp_result* result,
+                                         const rlvi_fp_dist* dist, void* stream) {
+  RLVI_REQUIRE(ctx && residuals && weights && e_work && result, "null pointer");
+  RLVI_REQUIRE(n > 0, "n must be positive");
+  RLVI_REQUIRE(maxiter >= 1, "maxiter must be >= 1");
+  RlviDeviceGuard guard(ctx->device);
+  FpParams<float> p;
+  memset(&p, 0, sizeof(p));
+  p.residuals = residuals;
+  p.pi_out = weights;
+  p.e = e_work;
+  p.n = n;
+  p.tol = double(tol);
+  p.maxiter = maxiter;
+  p.result = result;
+  int rc = fill_dist(p, dist, n);
+  if (rc != RLVI_OK) return rc;
+  const bool vec = rlvi_aligned16(residuals) && rlvi_aligned16(weights) && rlvi_aligned16(e_work);
+  const int64_t chunks = vec ? (n + 3) / 4 : n;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return vec ? launch_fp(ctx, fp_kernel_deep_f32<true>, p, chunks, st)
+             : launch_fp(ctx, fp_kernel_deep_f32<false>, p, chunks, st);
+}
