@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- RLVI E+M step throughput on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W     # N > 1 (the driver's launch)
+    python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
+
+Workload (SURVEY.md section 8d, configs[1]): logistic model, N = 2^26 samples x d = 64 features FP64, 30 %
+label corruption, synthetic, generated on the device.  One STEP = one E+M pass over all samples:
+  (1) loss pass      rlvi_loss_f64(LOGISTIC_CE)   reads X, y -> writes e = exp(-loss)
+  (2) E-step         rlvi_fixed_point_f64         K_fp passes over e until the reference's stop rule
+                                                  (tol 1e-3, maxiter 100) fires, then writes pi
+  (3) statistics     rlvi_weighted_moments_f64    reads X, pi -> S0, X^T pi, X^T Pi X  (+ all-reduce, N > 1)
+N > 1 shards the samples (strong scaling: the same 2^26 samples over N GPUs); the fixed point exchanges its
+three partial sums per pass inside the kernel over NVLink peer memory, the statistics are all-reduced by NCCL.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rlvi_em_step_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=26, help="total samples = 2^log2n (default: the named config)")
+    ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--cpu-log2n", type=int, default=22, help="bounded CPU sample for cpu_baseline / reference arm")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sample NVML during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference's E+M step (reference is pure Python/NumPy)
+# --------------------------------------------------------------------------------------------------
+def cpu_em_step_bench(log2n, d, steps, warmup):
+    import numpy as np
+    from oracle import rlvi_np
+    from rlvi_b200 import synth
+
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = 1
+    n = 1 << log2n
+    X, y, theta = synth.logistic_data(n, d, seed=0)
+    params = np.concatenate([[0.0], theta])
+    iters = None
+    for _ in range(warmup):
+        iters = rlvi_np.em_step_logistic(X, y, params)["iters"]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        iters = rlvi_np.em_step_logistic(X, y, params)["iters"]
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "cores": int(blas_threads), "kind": "port",
+            "sample": f"oracle.rlvi_np.em_step_logistic (NumPy restatement of rlvi.py:8-20 + utils.py:19-21,36-38) on "
+                      f"N=2^{log2n} x d={d} FP64 of the same synthetic workload, {steps} step(s) of {dt:.2f} s, "
+                      f"{iters} fixed-point passes; BLAS threads={blas_threads}, os.cpu_count()={os.cpu_count()}"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warmup = 1 if args.warmup > 0 else 0
+    cb, dt = cpu_em_step_bench(args.cpu_log2n, args.d, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"logistic E+M step, CPU sample N=2^{args.cpu_log2n}, d={args.d}, 30% label corruption "
+                                   f"(bounded sample of the N=2^{args.log2n} workload)"},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    from rlvi_b200 import _lib, dist as rdist, ops, synth
+
+    _lib.load()                                     # no CPU fallback: fail loudly
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = rdist.ShardGroup.create(dev) if world > 1 else None
+
+    n_total = 1 << args.log2n
+    d = args.d
+    lo, hi = rdist.shard_bounds(n_total, rank, world)
+    n = hi - lo
+    X, y, theta = synth.logistic_shard_torch(n, d, dev, seed=1234 + rank)
+    if world > 1:                                    # every rank needs the same theta*
+        torch.distributed.broadcast(theta, 0)
+    params = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), theta]).contiguous()
+    e = torch.empty(n, dtype=torch.float64, device=dev)
+    pi = torch.empty(n, dtype=torch.float64, device=dev)
+    res = torch.empty(5, dtype=torch.float64, device=dev)
+    mom = torch.zeros(_lib.load().rlvi_moments_out_doubles(d), dtype=torch.float64, device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+
+    def step(k=None):
+        if k is not None:
+            ev[k][0].record()
+        ops.loss(ops.LOSS_LOGISTIC_CE, X, params, y=y, intercept=True, want_losses=False, want_e=True, e_out=e)
+        if k is not None:
+            ev[k][1].record()
+        ops.fixed_point(None, e_work=e, out=pi, result=res, dist=group.fp_dist(n_total) if group else None)
+        if k is not None:
+            ev[k][2].record()
+        ops.weighted_moments(X, pi, out=mom)
+        if group:
+            group.all_reduce(mom)
+        if k is not None:
+            ev[k][3].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    fp = ops.read_result(res)
+    sampler = ClockSampler(local)
+    launches0 = ops.launch_count(local)
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    t_begin.record()
+    for k in range(args.steps):
+        step(k)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ops.launch_count(local) - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t)
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # per-kernel averages (this rank) and the roofline of the dominant kernel
+    kms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(3)] for k in range(args.steps)]).mean(axis=0)
+    k_fp = fp["iters"]
+    alg_bytes = {"loss_kernel": n * (d * 8 + 8 + 8), "fp_kernel_f64": n * 8 * (k_fp + 1) + n * 8,
+                 "gram64_kernel": n * (d * 8 + 8)}
+    names = list(alg_bytes)
+    kernels = {nm: {"ms": float(kms[i]), "algorithmic_bytes": int(alg_bytes[nm]),
+                    "GBps": alg_bytes[nm] / (kms[i] * 1e-3) / 1e9} for i, nm in enumerate(names)}
+    dom = names[int(np.argmax(kms))]
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "step_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak * (world if world > 1 else 1),
+                "kernels": kernels}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(dom)
+        except Exception:
+            pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"logistic E+M step (loss pass + epsilon fixed point + pi-weighted X^T Pi X), "
+                                   f"N=2^{args.log2n} samples x d={d} FP64, 30% label corruption, sample-sharded over "
+                                   f"{world} GPU(s)",
+                       "n_total": n_total, "d": d, "fixed_point_passes": k_fp, "fixed_point_tol": 1e-3,
+                       "l2": "inputs larger than L2 (X shard %.1f GiB streamed twice per step)" % (n * d * 8 / 2 ** 30),
+                       "parallelism": f"sample-sharded dp{world}"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")}}
+
+    # ---- e2e: the same step through the host-buffer C-ABI call, H2D/D2H inside the timed region --------
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total)
+    if world > 1:
+        torch.distributed.barrier()
+    del X, y
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_em_step_bench(args.cpu_log2n, d, 1, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        group.close()
+        torch.distributed.destroy_process_group()
+
+
+def run_e2e(args, X, y, params, dev, world, rank, n_total):
+    """Host buffers in, host buffers out: every step copies this rank's X/y shard host->device from pinned
+    memory (inside rlvi_em_step_logistic_host), runs the three stages, and copies pi + statistics back."""
+    import psutil
+    import torch
+
+    from rlvi_b200 import ops
+
+    n, d = X.shape
+    need = n * (d + 2) * 8
+    avail = psutil.virtual_memory().available // max(world, 1)
+    n_e2e = n
+    while n_e2e * (d + 2) * 8 > 0.6 * avail and n_e2e > 1024:
+        n_e2e //= 2
+    Xh = torch.empty((n_e2e, d), dtype=torch.float64, pin_memory=True)
+    yh = torch.empty(n_e2e, dtype=torch.float64, pin_memory=True)
+    pih = torch.empty(n_e2e, dtype=torch.float64, pin_memory=True)
+    Xh.copy_(X[:n_e2e])
+    yh.copy_(y[:n_e2e])
+    ph = params.cpu()
+    torch.cuda.synchronize()
+    if world > 1:
+        # the host entry point is single-GPU (one shard per process); ranks run their shards side by side
+        torch.distributed.barrier()
+    steps = max(1, args.e2e_steps)
+    ops.em_step_logistic_host(Xh, yh, ph, pi_out=pih, device=dev.index)      # warm-up (allocates the resident copy)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = ops.em_step_logistic_host(Xh, yh, ph, pi_out=pih, device=dev.index)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t)
+    nm = out["moments"].size
+    return {"value": n_e2e * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * (d + 1) * 8 + (d + 1) * 8),
+            "d2h_bytes_per_step": int(n_e2e * 8 + nm * 8 + 40), "ms_per_step": dt * 1e3, "steps": steps,
+            "n_per_gpu": int(n_e2e), "fixed_point_passes": out["result"]["iters"],
+            "note": "rlvi_em_step_logistic_host: pinned host X,y -> device (chunked, overlapped with the loss kernel), "
+                    "E-step, statistics, pi + statistics -> host"
+                    + ("" if n_e2e == n else f"; host RAM limited the e2e shard to {n_e2e} samples")
+                    + ("; N>1: independent shards, statistics not all-reduced in this call" if world > 1 else "")}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,18 @@ typedef struct rlvi_fp_dist {
 } rlvi_fp_dist;
 int rlvi_fp_dist_inbox_doubles(int world);   /* size of one rank's window, in doubles             */
 
+/* Peer windows for rlvi_fp_dist (one process per GPU; all three calls synchronise the device).
+ *   create: allocate + zero this rank's window, export its CUDA IPC handle (RLVI_IPC_HANDLE_BYTES bytes);
+ *   open:   `all_handles` = the handles of ranks 0..world-1 concatenated (gathered by the caller over any
+ *           transport); maps every peer window over NVLink and returns the DEVICE table of `world`
+ *           pointers to use as rlvi_fp_dist.peer_inbox (entry `rank` = own_window);
+ *   close:  unmap the peers, free the table and the window.                                            */
+#define RLVI_IPC_HANDLE_BYTES 64
+int rlvi_dist_window_create(rlvi_ctx* ctx, int world, void** window_out, unsigned char* handle_out);
+int rlvi_dist_window_open(rlvi_ctx* ctx, int rank, int world, void* own_window,
+                          const unsigned char* all_handles, void** peer_table_out);
+int rlvi_dist_window_close(rlvi_ctx* ctx, int rank, int world, void* own_window, void* peer_table);
+
 /* FP64 fixed point (STANDARD or ONLINE).
  *   losses   [n]  per-sample loss l_i, or NULL when `e_work` already holds e_i = exp(-l_i)
  *   scale    device scalar s or NULL (=1): the kernel uses e_i = exp(-s * l_i); lets the caller fold

@@ -1,0 +1,30 @@
+"""Drop-in for the RLVI pieces of the reference's `online-learning/main.py`:
+
+    update_weights_rlvi(losses, tol=1e-3, maxiter=100)     main.py:45-58
+    cross_entropy(log_proba, targets)                      main.py:84-85
+
+As in the reference every batch starts from pi = 0.5: nothing is carried across batches (quirk Q11).
+NumPy in -> NumPy out; CUDA tensors in -> CUDA tensors out.  No CPU fallback.
+"""
+from __future__ import annotations
+
+from . import ops
+from ._host import as_device, to_caller
+
+__all__ = ["update_weights_rlvi", "cross_entropy"]
+
+
+def update_weights_rlvi(losses, tol=1e-3, maxiter=100):
+    """main.py:45-58 -- pi0 = 0.5; rho = avg/(1-avg); pi' = rho e/(1 + rho e); stop when
+    ||pi' - pi|| < tol; result divided by max(pi') * n."""
+    l, was_np = as_device(losses)
+    pi, _ = ops.fixed_point(l, variant=ops.FP_ONLINE, tol=tol, maxiter=maxiter)
+    return to_caller(pi, was_np)
+
+
+def cross_entropy(log_proba, targets):
+    """main.py:84-85 -- -t log_proba - (1-t) log_proba (== -log_proba whatever the label, quirk Q11);
+    the same two-term expression, evaluated on the device."""
+    lp, was_np = as_device(log_proba)
+    t, _ = as_device(targets, like=lp)
+    return to_caller(-t * lp - (1 - t) * lp, was_np)

@@ -1,0 +1,272 @@
+"""Device-tensor front end of the C ABI (include/rlvi_b200.h): one Python function per entry point.
+
+Every function takes CUDA `torch.Tensor`s (torch is the allocator / stream provider only), passes raw
+device pointers and the CURRENT torch stream to librlvi_b200.so, and returns tensors on the same device.
+Nothing here computes: there is no CPU fallback, and a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (FP_DEEP, FP_ONLINE, FP_STANDARD, LOSS_GAUSSIAN, LOSS_LOGISTIC_CE, LOSS_PCA, LOSS_SOFTPLUS,
+                   LOSS_SQDIST, LOSS_SQRES)
+
+__all__ = ["FP_STANDARD", "FP_ONLINE", "FP_DEEP", "LOSS_LOGISTIC_CE", "LOSS_SOFTPLUS", "LOSS_SQRES",
+           "LOSS_SQDIST", "LOSS_PCA", "LOSS_GAUSSIAN", "fixed_point", "fixed_point_deep", "shift_sum", "loss",
+           "weighted_moments", "split_moments", "logistic_grad", "wce_fwd_bwd", "fn_threshold", "read_result",
+           "em_step_logistic_host", "launch_count"]
+
+_RESULT_DTYPE = np.dtype([("eps", "<f8"), ("rho", "<f8"), ("sum_pi", "<f8"), ("err", "<f8"), ("iters", "<i4"),
+                          ("converged", "<i4")])
+assert _RESULT_DTYPE.itemsize == C.sizeof(_lib.FpResult) == 40
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("rlvi_b200.ops works on CUDA tensors only (there is no CPU path)")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous CUDA tensor of dtype {dtype} (got {t.dtype}, "
+                        f"cuda={t.is_cuda}, contiguous={t.is_contiguous()})")
+    return t
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def launch_count(device=0) -> int:
+    """Kernels launched by the library on `device` since its context was created."""
+    return _lib.context(int(device)).launches
+
+
+def read_result(result: torch.Tensor) -> dict:
+    """Copy a device rlvi_fp_result (5 doubles = 40 bytes) to the host (synchronises the stream)."""
+    raw = result.cpu().numpy().view(np.uint8)[:40].view(_RESULT_DTYPE)[0]
+    out = {k: raw[k].item() for k in _RESULT_DTYPE.names}
+    if out["iters"] < 0:
+        raise _lib.RlviError("fixed-point kernel aborted: a grid/peer barrier timed out")
+    return out
+
+
+def fixed_point(losses=None, *, e_work=None, scale=None, variant=FP_STANDARD, tol=1e-3, maxiter=100, out=None,
+                result=None, dist=None):
+    """rlvi_fixed_point_f64.  Returns (pi, result_tensor); `result_tensor` stays on the device (see
+    `read_result`).  With `losses=None`, `e_work` must already hold e_i = exp(-l_i)."""
+    ref = losses if losses is not None else e_work
+    dev = _dev(ref)
+    f64 = torch.float64
+    losses = _chk(losses, f64, "losses")
+    n = ref.numel()
+    if e_work is None:
+        e_work = torch.empty(n, dtype=f64, device=ref.device)
+    _chk(e_work, f64, "e_work")
+    if out is None:
+        out = torch.empty(n, dtype=f64, device=ref.device)
+    _chk(out, f64, "out")
+    _chk(scale, f64, "scale")
+    if result is None:
+        result = torch.empty(5, dtype=f64, device=ref.device)
+    ctx = _lib.context(dev)
+    dptr = C.byref(dist) if dist is not None else None
+    rc = ctx.lib.rlvi_fixed_point_f64(ctx.handle, int(variant), _p(losses), _p(scale), _p(e_work), n, float(tol),
+                                      int(maxiter), _p(out), _p(result), dptr, _stream(dev))
+    _lib.check(rc, "rlvi_fixed_point_f64")
+    return out, result
+
+
+def fixed_point_deep(residuals, weights, *, e_work=None, tol=1e-3, maxiter=40, result=None, dist=None):
+    """rlvi_fixed_point_deep_f32: in place on `residuals` and `weights` (train_rlvi.py:14-38)."""
+    dev = _dev(residuals)
+    f32 = torch.float32
+    _chk(residuals, f32, "residuals")
+    _chk(weights, f32, "weights")
+    n = residuals.numel()
+    if weights.numel() != n:
+        raise ValueError("residuals and weights must have the same length")
+    if e_work is None:
+        e_work = torch.empty(n, dtype=f32, device=residuals.device)
+    if result is None:
+        result = torch.empty(5, dtype=torch.float64, device=residuals.device)
+    ctx = _lib.context(dev)
+    dptr = C.byref(dist) if dist is not None else None
+    rc = ctx.lib.rlvi_fixed_point_deep_f32(ctx.handle, _p(residuals), _p(weights), _p(e_work), n, float(tol),
+                                           int(maxiter), _p(result), dptr, _stream(dev))
+    _lib.check(rc, "rlvi_fixed_point_deep_f32")
+    return result
+
+
+def shift_sum(losses, shift, c, *, pi_out=None, out=None):
+    """rlvi_shift_sum_f64: out[0] = sum_i t_i/(c+t_i), t_i = exp(-l_i + shift) (rlvi.py:34-39)."""
+    dev = _dev(losses)
+    _chk(losses, torch.float64, "losses")
+    _chk(pi_out, torch.float64, "pi_out")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=losses.device)
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_shift_sum_f64(ctx.handle, _p(losses), losses.numel(), float(shift), float(c), _p(pi_out),
+                                    _p(out), _stream(dev))
+    _lib.check(rc, "rlvi_shift_sum_f64")
+    return out
+
+
+def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=True, want_e=False,
+         losses_out=None, e_out=None, wsum_out=None):
+    """rlvi_loss_f64.  Returns (losses | None, e | None, wsum | None)."""
+    dev = _dev(X)
+    f64 = torch.float64
+    _chk(X, f64, "X")
+    if X.dim() != 2:
+        raise ValueError("X must be [n, d]")
+    n, d = X.shape
+    _chk(params, f64, "params")
+    _chk(y, f64, "y")
+    _chk(weights, f64, "weights")
+    if want_losses and losses_out is None:
+        losses_out = torch.empty(n, dtype=f64, device=X.device)
+    if want_e and e_out is None:
+        e_out = torch.empty(n, dtype=f64, device=X.device)
+    if weights is not None and wsum_out is None:
+        wsum_out = torch.empty(2, dtype=f64, device=X.device)
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_loss_f64(ctx.handle, int(kind), 1 if intercept else 0, _p(X), _p(y), n, d, _p(params),
+                               _p(weights), _p(losses_out), _p(e_out), _p(wsum_out), _stream(dev))
+    _lib.check(rc, "rlvi_loss_f64")
+    return losses_out, e_out, wsum_out
+
+
+def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None):
+    """rlvi_weighted_moments_f64.  Returns the flat device buffer [S0, Swy, S1(d), Sy(d), G(d*d)];
+    `split_moments` gives views."""
+    dev = _dev(X)
+    f64 = torch.float64
+    _chk(X, f64, "X")
+    n, d = X.shape
+    _chk(weights, f64, "weights")
+    _chk(y, f64, "y")
+    ctx = _lib.context(dev)
+    if out is None:
+        out = torch.zeros(ctx.lib.rlvi_moments_out_doubles(d), dtype=f64, device=X.device)
+    rc = ctx.lib.rlvi_weighted_moments_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
+                                           1 if want_gram else 0, _p(out), _stream(dev))
+    _lib.check(rc, "rlvi_weighted_moments_f64")
+    return out
+
+
+def split_moments(out, d):
+    """Views into the flat moments buffer: dict(S0, Swy, S1, Sy, G)."""
+    return {"S0": out[0], "Swy": out[1], "S1": out[2:2 + d], "Sy": out[2 + d:2 + 2 * d],
+            "G": out[2 + 2 * d:2 + 2 * d + d * d].view(d, d)}
+
+
+def logistic_grad(X, y, weights, params, *, out=None):
+    """rlvi_logistic_grad_f64: [sum c, X^T c], c = w (sigmoid(b + x.theta) - y) (utils.py:40-41)."""
+    dev = _dev(X)
+    f64 = torch.float64
+    _chk(X, f64, "X")
+    n, d = X.shape
+    _chk(y, f64, "y")
+    _chk(weights, f64, "weights")
+    _chk(params, f64, "params")
+    if out is None:
+        out = torch.empty(d + 1, dtype=f64, device=X.device)
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_logistic_grad_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, _p(params), _p(out),
+                                        _stream(dev))
+    _lib.check(rc, "rlvi_logistic_grad_f64")
+    return out
+
+
+def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=True, want_per_sample=False,
+                want_correct=False):
+    """rlvi_wce_fwd_bwd_f32.  Returns dict(loss [1], dlogits | None, per_sample | None, correct | None)."""
+    dev = _dev(logits)
+    f32 = torch.float32
+    _chk(logits, f32, "logits")
+    b, c = logits.shape
+    _chk(labels, torch.int64, "labels")
+    _chk(indexes, torch.int64, "indexes")
+    _chk(weights, f32, "weights")
+    _chk(residuals, f32, "residuals")
+    n_train = weights.numel()
+    if residuals.numel() != n_train:
+        raise ValueError("residuals and weights must have the same length")
+    if indexes is None and n_train < b:
+        raise ValueError("identity indexes need n_train >= batch")
+    out_loss = torch.empty(1, dtype=f32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    per = torch.empty(b, dtype=f32, device=logits.device) if want_per_sample else None
+    correct = torch.empty(2, dtype=torch.int32, device=logits.device) if want_correct else None
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_wce_fwd_bwd_f32(ctx.handle, _p(logits), _p(labels), _p(indexes), _p(weights), _p(residuals), b,
+                                      c, n_train, _p(per), _p(dlogits), _p(out_loss), _p(correct), _stream(dev))
+    _lib.check(rc, "rlvi_wce_fwd_bwd_f32")
+    return {"loss": out_loss, "dlogits": dlogits, "per_sample": per, "correct": correct}
+
+
+def fn_threshold(weights, alpha=0.05, prev_threshold=0.0, truncate=False, *, out=None):
+    """rlvi_fn_threshold_f32: false_negative_criterion (+ optional truncation), train_rlvi.py:41-49,102-103."""
+    dev = _dev(weights)
+    _chk(weights, torch.float32, "weights")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=weights.device)
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_fn_threshold_f32(ctx.handle, _p(weights), weights.numel(), float(alpha),
+                                       float(prev_threshold), 1 if truncate else 0, _p(out), _stream(dev))
+    _lib.check(rc, "rlvi_fn_threshold_f32")
+    return out
+
+
+def em_step_logistic_host(X, y, params, *, tol=1e-3, maxiter=100, want_pi=True, device=0, pi_out=None,
+                          moments_out=None):
+    """rlvi_em_step_logistic_host on HOST arrays (NumPy or CPU torch tensors, FP64, C-contiguous; pinned
+    memory makes the copies asynchronous).  Returns dict(pi, moments, result)."""
+    def host_ptr(a, name):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda or a.dtype != torch.float64 or not a.is_contiguous():
+                raise TypeError(f"{name}: need a contiguous CPU float64 tensor")
+            return C.c_void_p(a.data_ptr()), tuple(a.shape)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return C.c_void_p(a.ctypes.data), a.shape, a
+
+    hx = host_ptr(X, "X")
+    hy = host_ptr(y, "y")
+    hp = host_ptr(params, "params")
+    n, d = hx[1]
+    if hy[1] != (n,) or hp[1] != (d + 1,):
+        raise ValueError("shape mismatch: X [n,d], y [n], params [d+1]")
+    ctx = _lib.context(int(device))
+    nm = ctx.lib.rlvi_moments_out_doubles(d)
+    if want_pi and pi_out is None:
+        pi_out = np.empty(n, dtype=np.float64)
+    if moments_out is None:
+        moments_out = np.empty(nm, dtype=np.float64)
+    res = _lib.FpResult()
+
+    def out_ptr(a):
+        if a is None:
+            return None
+        return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
+
+    rc = ctx.lib.rlvi_em_step_logistic_host(ctx.handle, hx[0], hy[0], n, d, hp[0], float(tol), int(maxiter),
+                                            out_ptr(pi_out) if want_pi else None, out_ptr(moments_out),
+                                            C.byref(res))
+    _lib.check(rc, "rlvi_em_step_logistic_host")
+    if res.iters < 0:
+        raise _lib.RlviError("fixed-point kernel aborted: a grid barrier timed out")
+    return {"pi": pi_out if want_pi else None, "moments": moments_out,
+            "result": {"eps": res.eps, "rho": res.rho, "sum_pi": res.sum_pi, "err": res.err, "iters": res.iters,
+                       "converged": res.converged}}

@@ -1,0 +1,199 @@
+"""Drop-in for the reference's `standard-learning/rlvi.py`: same function names, positional order and
+keyword defaults, running on librlvi_b200.so.
+
+    update_weights(losses, tol=1e-3, maxiter=100)                       rlvi.py:8-20
+    update_weights_constrained(losses, n_eff, tol=1e-3, maxiter=100)    rlvi.py:23-43
+    mean(sample, maxiter=100, tol=1e-3)                                 rlvi.py:46-65
+    linear_regression(X, y, maxiter=100, tol=1e-3)                      rlvi.py:68-89
+    logistic_regression(X, y, maxiter=100, tol=1e-2)                    rlvi.py:92-108
+    pca(sample, maxiter=100, tol=1e-2, theta_init=None)                 rlvi.py:111-125
+    covariance(sample, eps, maxiter=100, tol=1e-2)                      rlvi.py:128-144
+
+Array arguments may be NumPy arrays (copied to the GPU, NumPy returned -- the reference's calling
+convention) or CUDA FP64 `torch.Tensor`s (used in place, tensors returned, nothing leaves the device
+except the d-sized quantities the outer stop tests need).  All N-sized work -- per-sample losses, the
+epsilon fixed point, the pi-weighted statistics -- runs in the CUDA kernels; the host (or torch on the
+device) only does the O(d^3) algebra: the d x d solve / eigendecomposition and the stop tests.
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy import optimize as _opt
+
+from . import ops
+from . import utils as _utils
+from ._host import as_device, to_caller
+
+__all__ = ["update_weights", "update_weights_constrained", "mean", "linear_regression", "logistic_regression",
+           "pca", "covariance"]
+
+
+# --------------------------------------------------------------------------------------------------
+# E-step
+# --------------------------------------------------------------------------------------------------
+def update_weights(losses, tol=1e-3, maxiter=100):
+    """rlvi.py:8-20 -- the epsilon fixed point; one persistent kernel, loop exit decided on the device."""
+    l, was_np = as_device(losses)
+    pi, _ = ops.fixed_point(l, variant=ops.FP_STANDARD, tol=tol, maxiter=maxiter)
+    return to_caller(pi, was_np)
+
+
+def update_weights_constrained(losses, n_eff, tol=1e-3, maxiter=100):
+    """rlvi.py:23-43 -- the fixed point, then (if sum pi < n_eff) the KKT shift found by SciPy's
+    unbounded Brent exactly as in the reference; only the objective's O(N) sum is a device call
+    (SURVEY.md H4)."""
+    l, was_np = as_device(losses)
+    n = l.numel()
+    pi, res = ops.fixed_point(l, variant=ops.FP_STANDARD, tol=tol, maxiter=maxiter)
+    sum_pi = pi.sum().item()                                    # rlvi.py:32  np.sum(weights) < n_eff
+    if sum_pi < n_eff:
+        c = (n - n_eff) / n_eff
+        acc = torch.empty(1, dtype=torch.float64, device=l.device)
+
+        def shift_obj(s):                                        # rlvi.py:34-39
+            ops.shift_sum(l, s, c, out=acc)
+            return np.square(acc.item() - n_eff)
+
+        shift = _opt.minimize_scalar(shift_obj)["x"]             # rlvi.py:41
+        ops.shift_sum(l, shift, c, pi_out=pi, out=acc)           # rlvi.py:42
+    return to_caller(pi, was_np)
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers shared by the outer loops
+# --------------------------------------------------------------------------------------------------
+def _rel_change(new, old):
+    """||new - old|| / ||old|| on the host (d-sized)."""
+    return float(torch.linalg.norm(new - old) / torch.linalg.norm(old))
+
+
+def _estep_scaled(r2, wsum, e_work, pi):
+    """losses = 0.5 * r2 / sigma2, sigma2 = (pi . r2) / sum(pi) (rlvi.py:50-51,58-59,73-74,82-83) folded
+    into the fixed-point kernel as a device scalar: no host round trip between loss pass and E-step."""
+    scale = 0.5 * wsum[1:2] / wsum[0:1]                          # 0.5 / sigma2, stays on the device
+    ops.fixed_point(r2, scale=scale, e_work=e_work, out=pi, variant=ops.FP_STANDARD)
+    return pi
+
+
+# --------------------------------------------------------------------------------------------------
+# outer EM loops
+# --------------------------------------------------------------------------------------------------
+def mean(sample, maxiter=100, tol=1e-3):
+    """rlvi.py:46-65."""
+    X, was_np = as_device(sample)
+    n, d = X.shape
+    pi = torch.ones(n, dtype=torch.float64, device=X.device)
+    e_work = torch.empty_like(pi)
+    r2 = torch.empty_like(pi)
+    mom = None
+
+    def mstep():
+        nonlocal mom
+        mom = ops.weighted_moments(X, pi, want_gram=False, out=mom)
+        m = ops.split_moments(mom, d)
+        theta = m["S1"] / m["S0"]                                # rlvi.py:48,56
+        _, _, wsum = ops.loss(ops.LOSS_SQDIST, X, theta, weights=pi, losses_out=r2)   # rlvi.py:49-50,57-58
+        return theta, wsum
+
+    theta, wsum = mstep()
+    for _ in range(maxiter):
+        _estep_scaled(r2, wsum, e_work, pi)                      # rlvi.py:54
+        prev = theta
+        theta, wsum = mstep()
+        if _rel_change(theta, prev) <= tol:                      # rlvi.py:62-64
+            break
+    return to_caller(theta, was_np)
+
+
+def _gpu_sym_solve(G, b):
+    """theta = argmin ||sqrt(Pi) (X theta - y)||.  The reference calls scipy lstsq (LAPACK gelsd) on the
+    N x d scaled design (rlvi.py:71,80); this is the same minimiser from the d x d statistics
+    G = X^T Pi X, b = X^T Pi y, through an eigen-decomposition pseudo-inverse so that rank-deficient
+    designs give the minimum-norm solution as gelsd does."""
+    evals, evecs = torch.linalg.eigh(G)
+    cutoff = torch.finfo(G.dtype).eps * evals.abs().max()
+    inv = torch.where(evals.abs() > cutoff, 1.0 / evals, torch.zeros_like(evals))
+    return evecs @ (inv * (evecs.T @ b))
+
+
+def linear_regression(X, y, maxiter=100, tol=1e-3):
+    """rlvi.py:68-89."""
+    Xd, was_np = as_device(X)
+    yd, _ = as_device(y, like=Xd)
+    n, d = Xd.shape
+    pi = torch.ones(n, dtype=torch.float64, device=Xd.device)
+    e_work = torch.empty_like(pi)
+    r2 = torch.empty_like(pi)
+    mom = None
+
+    def mstep():
+        nonlocal mom
+        mom = ops.weighted_moments(Xd, pi, y=yd, out=mom)
+        m = ops.split_moments(mom, d)
+        theta = _gpu_sym_solve(m["G"], m["Sy"])                  # rlvi.py:70-71,79-80
+        _, _, wsum = ops.loss(ops.LOSS_SQRES, Xd, theta, y=yd, weights=pi, losses_out=r2)   # rlvi.py:72-73
+        return theta, wsum
+
+    theta, wsum = mstep()
+    for _ in range(maxiter):
+        _estep_scaled(r2, wsum, e_work, pi)                      # rlvi.py:77
+        prev = theta
+        theta, wsum = mstep()
+        if _rel_change(theta, prev) <= tol:                      # rlvi.py:85-87
+            break
+    return to_caller(theta, was_np)
+
+
+def logistic_regression(X, y, maxiter=100, tol=1e-2, mstep="sklearn"):
+    """rlvi.py:92-108.  `mstep="sklearn"` (reference default, line 96/103: L2-regularised fit with C = 100
+    and the label-independent softplus loss of utils.sklearn_log_reg) or `mstep="mm"` (the alternative the
+    reference keeps commented at lines 95/102: utils.mm_log_reg with the true cross-entropy)."""
+    Xd, was_np = as_device(X)
+    yd, _ = as_device(y, like=Xd)
+    fit = _utils.sklearn_log_reg if mstep == "sklearn" else _utils.mm_log_reg
+    n = Xd.shape[0]
+    pi = torch.ones(n, dtype=torch.float64, device=Xd.device)
+    theta, losses = fit(Xd, yd, pi)
+    e_work = torch.empty_like(pi)
+    for _ in range(maxiter):
+        ops.fixed_point(losses, e_work=e_work, out=pi, variant=ops.FP_STANDARD)   # rlvi.py:100
+        prev = theta
+        theta, losses = fit(Xd, yd, pi)
+        if _rel_change(theta, prev) <= tol:                      # rlvi.py:105-107
+            break
+    return to_caller(theta, was_np)
+
+
+def pca(sample, maxiter=100, tol=1e-2, theta_init=None):
+    """rlvi.py:111-125."""
+    X, was_np = as_device(sample)
+    n = X.shape[0]
+    pi = torch.ones(n, dtype=torch.float64, device=X.device)
+    t0 = None if theta_init is None else as_device(theta_init, like=X)[0]
+    theta, losses = _utils.pca(X, pi, t0)
+    e_work = torch.empty_like(pi)
+    for _ in range(maxiter):
+        ops.fixed_point(losses, e_work=e_work, out=pi, variant=ops.FP_STANDARD)   # rlvi.py:117
+        prev = theta
+        theta, losses = _utils.pca(X, pi)
+        if _rel_change(theta, prev) <= tol:                      # rlvi.py:121-123
+            break
+    return to_caller(theta, was_np)
+
+
+def covariance(sample, eps, maxiter=100, tol=1e-2):
+    """rlvi.py:128-144."""
+    X, was_np = as_device(sample)
+    n = X.shape[0]
+    n_eff = n * (1 - eps)                                        # rlvi.py:130
+    pi = torch.ones(n, dtype=torch.float64, device=X.device)
+    cov, losses = _utils.covariance(X, pi)
+    for _ in range(maxiter):
+        pi = update_weights_constrained(losses, n_eff)           # rlvi.py:135
+        prev = cov
+        cov, losses = _utils.covariance(X, pi)
+        if float(torch.linalg.norm(cov - prev) / torch.linalg.norm(prev)) <= tol:   # rlvi.py:140 (Frobenius)
+            break
+    return to_caller(cov, was_np)

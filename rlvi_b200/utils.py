@@ -1,0 +1,201 @@
+"""Drop-in for the reference's `standard-learning/utils.py` (per-sample losses + weighted M-steps):
+
+    sigmoid(x)                                      utils.py:7-16
+    cross_entropy(X, theta, y)                      utils.py:19-21
+    clf_predict(X, theta)                           utils.py:24-29
+    mm_log_reg(X, y, weights)                       utils.py:32-58
+    sklearn_log_reg(X, y, weights, reg_coeff=1e2)   utils.py:61-73
+    pca(samples, weights, theta=None)               utils.py:76-89
+    covariance(samples, weights, mean=None)         utils.py:92-108
+
+Same signatures and return values `(theta, losses)`.  NumPy in -> NumPy out, CUDA tensors in -> CUDA
+tensors out.  Every pass over the N samples is a CUDA kernel of librlvi_b200.so; the d x d algebra
+(inverse, eigen-decomposition, Cholesky) is done by torch on the device.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._host import as_device, to_caller
+
+__all__ = ["sigmoid", "cross_entropy", "clf_predict", "mm_log_reg", "sklearn_log_reg", "pca", "covariance"]
+
+
+def sigmoid(x):
+    """utils.py:7-16 -- overflow-free logistic function.  A d-sized / scalar helper in the reference's
+    callers; evaluated with torch on whichever device holds `x` (the N-sized sigmoid of the M-step lives
+    inside rlvi_logistic_grad_f64)."""
+    if isinstance(x, torch.Tensor):
+        z = torch.exp(-torch.abs(x))
+        return torch.where(x >= 0, torch.ones_like(z), z) / (1 + z)
+    t, was_np = as_device(np.atleast_1d(x))
+    z = torch.exp(-torch.abs(t))
+    r = torch.where(t >= 0, torch.ones_like(z), z) / (1 + z)
+    r = r.cpu().numpy()
+    return r.reshape(np.shape(x)) if np.ndim(x) else float(r[0])
+
+
+def cross_entropy(X, theta, y):
+    """utils.py:19-21 -- l = -y phi + phi + log1p(exp(-phi)), phi = X theta.  As in the reference, X is
+    the design matrix theta applies to (mm_log_reg passes the ones-augmented matrix)."""
+    Xd, was_np = as_device(X)
+    td, _ = as_device(theta, like=Xd)
+    yd, _ = as_device(y, like=Xd)
+    losses, _, _ = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, td, y=yd, intercept=False)
+    return to_caller(losses, was_np)
+
+
+def clf_predict(X, theta):
+    """utils.py:24-29 -- 0/1 predictions of [1, X] theta (sign of the linear predictor)."""
+    Xd, was_np = as_device(X)
+    td, _ = as_device(theta, like=Xd)
+    # softplus(phi) > log 2  <=>  phi > 0  <=>  sigmoid(phi) > 0.5
+    sp, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, td, intercept=True)
+    pred = (sp > math.log(2.0)).to(torch.float64)
+    return to_caller(pred, was_np)
+
+
+def _augmented_gram(X, y, weights, mom=None):
+    """[[S0, S1^T], [S1, G]] = [1, X]^T diag(w) [1, X] from one statistics pass."""
+    d = X.shape[1]
+    mom = ops.weighted_moments(X, weights, y=None, out=mom)
+    m = ops.split_moments(mom, d)
+    A = torch.empty((d + 1, d + 1), dtype=torch.float64, device=X.device)
+    A[0, 0] = m["S0"]
+    A[0, 1:] = m["S1"]
+    A[1:, 0] = m["S1"]
+    A[1:, 1:] = m["G"]
+    return A
+
+
+def mm_log_reg(X, y, weights):
+    """utils.py:32-58 -- MM logistic regression: Q = 1/4 [1,X]^T Pi [1,X] once (one statistics pass),
+    then theta <- theta - Q^-1 [1,X]^T (pi * (sigmoid - y)) (one gradient pass each) until
+    ||delta theta|| <= 1e-2; returns (theta [d+1] intercept first, cross-entropy losses)."""
+    Xd, was_np = as_device(X)
+    yd, _ = as_device(y, like=Xd)
+    wd, _ = as_device(weights, like=Xd)
+    d = Xd.shape[1]
+    Q_inv = torch.linalg.inv(0.25 * _augmented_gram(Xd, yd, wd))         # utils.py:36-38
+    theta0 = torch.zeros(d + 1, dtype=torch.float64, device=Xd.device)   # utils.py:35
+    g = torch.empty(d + 1, dtype=torch.float64, device=Xd.device)
+
+    def step(theta):                                                      # utils.py:40-41,45,50
+        ops.logistic_grad(Xd, yd, wd, theta, out=g)
+        return theta - Q_inv @ g
+
+    theta1 = step(theta0)
+    n_grad = 1
+    while float(torch.linalg.norm(theta1 - theta0)) > 1e-2:              # utils.py:47
+        theta0 = theta1
+        theta1 = step(theta0)
+        n_grad += 1
+    mm_log_reg.last_n_grad = n_grad
+    losses, _, _ = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, theta1, y=yd, intercept=True)   # utils.py:56
+    return to_caller(theta1, was_np), to_caller(losses, was_np)
+
+
+def sklearn_log_reg(X, y, weights, reg_coeff=1e2, gtol=1e-8, max_passes=500):
+    """utils.py:61-73.  Reproduces the function's observable behaviour:
+      * `weights` is normalised IN PLACE by its maximum (line 66, quirk Q3);
+      * theta = [intercept, coef] minimises liblinear's objective for `LogisticRegression(C=reg_coeff,
+        solver="liblinear")` with sample weights:  1/2 ||[b, w]||^2 + C sum_i pi_i logloss_i
+        (liblinear regularises the intercept too: intercept_scaling = 1);
+      * losses = -log P(class 0 | x) = softplus(b + x.w) for every row whatever its label (lines 62-64).
+    liblinear itself (third-party C++) is not re-implemented: the same convex
+    problem is solved on the device by majorise-minimise steps with the fixed curvature bound
+    I + C/4 [1,X]^T Pi [1,X] (one statistics pass, then one gradient pass per step) until the gradient
+    norm has dropped by `gtol`, which is tighter than liblinear's own stopping rule (tol = 1e-4), so the
+    two agree to liblinear's accuracy."""
+    Xd, was_np = as_device(X)
+    yd, _ = as_device(y, like=Xd)
+    if isinstance(weights, np.ndarray):
+        weights /= np.max(weights)                                        # utils.py:66, caller's array
+        wd, _ = as_device(weights, like=Xd)
+    else:
+        wd, _ = as_device(weights, like=Xd)
+        wd /= wd.max()
+    d = Xd.shape[1]
+    eye = torch.eye(d + 1, dtype=torch.float64, device=Xd.device)
+    H = eye + (0.25 * reg_coeff) * _augmented_gram(Xd, yd, wd)
+    H_inv = torch.linalg.inv(H)
+    theta = torch.zeros(d + 1, dtype=torch.float64, device=Xd.device)
+    g = torch.empty(d + 1, dtype=torch.float64, device=Xd.device)
+    g0 = None
+    for _ in range(max_passes):
+        ops.logistic_grad(Xd, yd, wd, theta, out=g)
+        grad = theta + reg_coeff * g
+        gn = float(torch.linalg.norm(grad))
+        if g0 is None:
+            g0 = gn
+        if gn <= gtol * max(g0, 1e-300):
+            break
+        theta = theta - H_inv @ grad
+    losses, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, theta, intercept=True)   # utils.py:70-71
+    return to_caller(theta, was_np), to_caller(losses, was_np)
+
+
+def _svd_flip_unit(v):
+    """sklearn's v-based svd_flip (largest-|.| entry positive) + utils.py:85 normalisation."""
+    k = torch.argmax(torch.abs(v))
+    v = v * torch.sign(v[k])
+    return v / torch.linalg.norm(v)
+
+
+def pca(samples, weights, theta=None):
+    """utils.py:76-89.  theta = top principal direction of the rows pi_i x_i after column-centring
+    (what `PCA(n_components=1).fit(diag(pi) @ X)` returns: quirk Q4 -- weights pi, not sqrt(pi)), from
+    G = sum pi_i^2 x_i x_i^T and m = sum pi_i x_i / N:  C = (G - N m m^T)/(N-1), top eigenvector, sklearn's
+    sign rule, unit norm.  losses_i = ||x_i||^2 - (x_i . theta)^2 (uncentred)."""
+    X, was_np = as_device(samples)
+    n, d = X.shape
+    if theta is None:
+        wd, _ = as_device(weights, like=X)
+        mom = ops.weighted_moments(X, wd, power=2)
+        m = ops.split_moments(mom, d)
+        mu = m["S1"] / n
+        Cm = (m["G"] - n * torch.outer(mu, mu)) / (n - 1)
+        _, evecs = torch.linalg.eigh(Cm)
+        theta_d = _svd_flip_unit(evecs[:, -1])
+    else:
+        theta_d, _ = as_device(theta, like=X)
+    losses, _, _ = ops.loss(ops.LOSS_PCA, X, theta_d)
+    return to_caller(theta_d, was_np), to_caller(losses, was_np)
+
+
+def _gaussian_params(mu, cov):
+    """[c, mu, U] for RLVI_LOSS_GAUSSIAN: U upper triangular with U^T U = cov^-1, c = log|cov| + d log 2pi.
+    Raises ValueError("Singular covariance matrix") like utils.py:98-100."""
+    d = mu.numel()
+    sign, logabsdet = torch.linalg.slogdet(cov)
+    if not (float(sign) > 0):
+        raise ValueError("Singular covariance matrix")
+    # cov = R R^T with R UPPER triangular (Cholesky of the index-reversed matrix), U = R^-1
+    J = torch.arange(d - 1, -1, -1, device=cov.device)
+    Lr, info = torch.linalg.cholesky_ex(cov[J][:, J])
+    if int(info) != 0:
+        raise ValueError("Singular covariance matrix")
+    R = Lr[J][:, J]
+    U = torch.linalg.solve_triangular(R, torch.eye(d, dtype=cov.dtype, device=cov.device), upper=True)
+    c = logabsdet + d * math.log(2 * math.pi)
+    return torch.cat([c.reshape(1), mu, torch.triu(U).reshape(-1)]).contiguous()
+
+
+def covariance(samples, weights, mean=None):
+    """utils.py:92-108.  mu = X^T pi / sum pi; cov = (X-mu)^T Pi (X-mu) / sum pi (from one statistics pass:
+    G/S0 - mu mu^T); losses = Gaussian NLL.  The `mean` argument is ignored, as in the reference (line 103)."""
+    X, was_np = as_device(samples)
+    wd, _ = as_device(weights, like=X)
+    n, d = X.shape
+    mom = ops.weighted_moments(X, wd)
+    m = ops.split_moments(mom, d)
+    mu = m["S1"] / m["S0"]
+    cov = m["G"] / m["S0"] - torch.outer(mu, mu)
+    cov = 0.5 * (cov + cov.T)
+    params = _gaussian_params(mu, cov)
+    losses, _, _ = ops.loss(ops.LOSS_GAUSSIAN, X, params)
+    return to_caller(cov, was_np), to_caller(losses, was_np)

@@ -1,0 +1,538 @@
+"""GPU parity tests proper: every C-ABI entry point (through rlvi_b200.ops / the drop-in modules, which
+call ONLY librlvi_b200.so for N-sized work) against the oracle on the same seeded inputs and against the
+golden vectors produced by the unmodified reference (tests/golden/, oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): 1e-9 relative for FP64 statistics and epsilon, 1e-5 for FP32
+posteriors and losses, identical selection masks.  Raw posteriors in the collapse regime
+are compared at max(1e-9, 8 ulp(1) / mean pi).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import deep_ref, rlvi_np
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-9
+F32_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from rlvi_b200 import _lib
+    _lib.load()                      # fail loudly if the extension is missing
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def cu(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+def relmax(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def pi_tol(ref_pi):
+    return max(F64_TOL, 8 * 2.0 ** -52 / max(float(np.mean(ref_pi)), 1e-300))
+
+
+# ==================================================================================================
+# E-step: fixed point
+# ==================================================================================================
+@pytest.mark.parametrize("tag", ["n40", "n1000", "n4096", "n16384"])
+def test_update_weights_golden(dev, tag):
+    from rlvi_b200 import ops, rlvi
+    g = load_golden("update_weights_" + tag)
+    pi = rlvi.update_weights(g["losses"])                      # NumPy in -> NumPy out
+    assert isinstance(pi, np.ndarray) and pi.dtype == np.float64
+    assert relmax(pi, g["pi"]) < pi_tol(g["pi"])
+    assert relmax(pi / pi.sum(), g["pi"] / g["pi"].sum()) < F64_TOL
+    # iteration count, eps and err against the oracle's trace of the same loop
+    _, eps, k, err = rlvi_np.fixed_point_trace(g["losses"])
+    _, res = ops.fixed_point(cu(g["losses"], dev))
+    r = ops.read_result(res)
+    assert r["iters"] == k
+    assert abs(r["eps"] - eps) <= F64_TOL * abs(eps)
+    assert abs(r["err"] - err) <= 1e-6 * err + 1e-15
+    assert abs(r["sum_pi"] - g["pi"].sum()) <= pi_tol(g["pi"]) * g["pi"].sum()
+
+
+def test_update_weights_tol_maxiter_negative_losses(dev):
+    from rlvi_b200 import ops, rlvi
+    g = load_golden("update_weights_neg")
+    pi = rlvi.update_weights(g["losses"], float(g["tol"]), int(g["maxiter"]))
+    assert relmax(pi, g["pi"]) < pi_tol(g["pi"])
+    _, res = ops.fixed_point(cu(g["losses"], dev), tol=float(g["tol"]), maxiter=int(g["maxiter"]))
+    r = ops.read_result(res)
+    assert r["iters"] == int(g["maxiter"]) and r["converged"] == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 1023, 1025, 300001])
+def test_fixed_point_ragged_and_unaligned(dev, n):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(n)
+    losses = 0.5 * rng.chisquare(1, size=n + 1)
+    ref, eps, k, err = rlvi_np.fixed_point_trace(losses[1:])
+    base = cu(losses, dev)
+    pi, res = ops.fixed_point(base[1:])                        # 8-byte aligned only -> scalar path
+    r = ops.read_result(res)
+    assert r["iters"] == k
+    assert relmax(pi.cpu().numpy(), ref) < pi_tol(ref)
+    pi2, res2 = ops.fixed_point(base[1:].clone())              # 16-byte aligned -> vector path
+    assert ops.read_result(res2)["iters"] == k
+    assert relmax(pi2.cpu().numpy(), ref) < pi_tol(ref)
+
+
+def test_fixed_point_scale_and_precomputed_e(dev):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(5)
+    r2 = rng.chisquare(1, size=50000) * 3.0
+    s = 0.37
+    ref, _, k, _ = rlvi_np.fixed_point_trace(s * r2)
+    scale = torch.tensor([s], dtype=torch.float64, device=dev)
+    pi, res = ops.fixed_point(cu(r2, dev), scale=scale)
+    assert ops.read_result(res)["iters"] == k
+    assert relmax(pi.cpu().numpy(), ref) < pi_tol(ref)
+    e = cu(np.exp(-(s * r2)), dev)
+    pi2, res2 = ops.fixed_point(None, e_work=e)
+    assert ops.read_result(res2)["iters"] == k
+    assert relmax(pi2.cpu().numpy(), ref) < pi_tol(ref)
+    # in-place: pi_out aliases losses
+    l = cu(s * r2, dev)
+    pi3, _ = ops.fixed_point(l, out=l)
+    assert relmax(pi3.cpu().numpy(), ref) < pi_tol(ref)
+
+
+def test_fixed_point_eps_equals_one_gives_zero_weights(dev):
+    """Quirk Q1: huge losses underflow mean(pi) so eps == 1.0, rho = inf, pi = 0 (the reference then
+    divides by zero downstream; the kernel reproduces the all-zero posteriors)."""
+    from rlvi_b200 import ops
+    losses = np.full(4096, 800.0)
+    with np.errstate(all="ignore"):
+        ref = rlvi_np.update_weights(losses)
+    pi, _ = ops.fixed_point(cu(losses, dev))
+    out = pi.cpu().numpy()
+    assert np.all(ref == 0.0) and np.all(out == 0.0)
+
+
+def test_online_fixed_point_golden(dev):
+    from rlvi_b200 import online
+    g = load_golden("online_n100")
+    res = online.cross_entropy(g["log_proba"], g["targets"])
+    assert np.array_equal(res, g["residuals"])
+    pi = online.update_weights_rlvi(g["residuals"])
+    assert relmax(pi, g["pi"]) < F64_TOL
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 100, 4097):
+        l = rng.exponential(1.0, size=n)
+        assert relmax(online.update_weights_rlvi(l), rlvi_np.update_weights_online(l)) < F64_TOL
+
+
+@pytest.mark.parametrize("tag", ["n50", "n3000"])
+def test_update_weights_constrained_golden(dev, tag):
+    from rlvi_b200 import rlvi
+    g = load_golden("constrained_" + tag)
+    pi = rlvi.update_weights_constrained(g["losses"], float(g["n_eff"]))
+    # Brent's own accuracy bounds the agreement: the constraint is met to ~1e-8
+    assert abs(pi.sum() - float(g["n_eff"])) < 1e-3 * float(g["n_eff"])
+    assert relmax(pi, g["pi"]) < 1e-6
+
+
+def test_shift_sum(dev):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(11)
+    l = rng.chisquare(2, size=77777)
+    s, c = 0.8, 0.43
+    t = np.exp(-l + s)
+    ref = t / (c + t)
+    pi = torch.empty(l.size, dtype=torch.float64, device=dev)
+    out = ops.shift_sum(cu(l, dev), s, c, pi_out=pi)
+    assert abs(out.item() - ref.sum()) < 1e-12 * ref.sum()
+    assert relmax(pi.cpu().numpy(), ref) < 1e-14
+
+
+# ==================================================================================================
+# per-sample losses
+# ==================================================================================================
+SHAPES = [(1, 1), (5, 2), (33, 3), (40, 10), (257, 31), (1000, 32), (1031, 64), (777, 65), (500, 100),
+          (300, 512), (130, 1000), (64, 1024)]
+
+
+@pytest.mark.parametrize("n,d", SHAPES)
+def test_losses_against_oracle(dev, n, d):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(1000 * n + d)
+    X = rng.normal(size=(n, d))
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    theta = rng.normal(size=d) / np.sqrt(d)
+    b = 0.3
+    w = rng.random(n)
+    Xd, yd, wd = cu(X, dev), cu(y, dev), cu(w, dev)
+    Xa = np.hstack([np.ones((n, 1)), X])
+    tb = np.concatenate([[b], theta])
+
+    # logistic CE with and without intercept (utils.py:19-21)
+    ref = rlvi_np.cross_entropy(Xa, tb, y)
+    l, e, ws = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, cu(tb, dev), y=yd, intercept=True, weights=wd, want_e=True)
+    assert relmax(l.cpu().numpy(), ref) < 1e-12
+    assert relmax(e.cpu().numpy(), np.exp(-ref)) < 1e-12
+    ws = ws.cpu().numpy()
+    assert abs(ws[0] - w @ ref) < 1e-12 * abs(w @ ref) and abs(ws[1] - w.sum()) < 1e-13 * w.sum()
+    l2, _, _ = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, cu(theta, dev), y=yd, intercept=False)
+    assert relmax(l2.cpu().numpy(), rlvi_np.cross_entropy(X, theta, y)) < 1e-12
+
+    # softplus (utils.py:62-64)
+    l3, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, cu(tb, dev), intercept=True)
+    assert relmax(l3.cpu().numpy(), rlvi_np.softplus_loss(X, tb)) < 1e-12
+
+    # squared residual (rlvi.py:72), squared distance (rlvi.py:49), PCA reconstruction (utils.py:77-79)
+    yr = X @ theta + rng.normal(size=n)
+    l4, _, _ = ops.loss(ops.LOSS_SQRES, Xd, cu(theta, dev), y=cu(yr, dev))
+    assert relmax(l4.cpu().numpy(), (yr - X @ theta) ** 2) < 1e-11
+    mu = rng.normal(size=d)
+    l5, _, _ = ops.loss(ops.LOSS_SQDIST, Xd, cu(mu, dev))
+    assert relmax(l5.cpu().numpy(), np.linalg.norm(mu - X, axis=1) ** 2) < 1e-12
+    v = theta / np.linalg.norm(theta)
+    l6, _, _ = ops.loss(ops.LOSS_PCA, Xd, cu(v, dev))
+    refp = rlvi_np.pca_losses(X, v)
+    assert np.max(np.abs(l6.cpu().numpy() - refp)) < 1e-12 * np.max(np.sum(X ** 2, axis=1))
+
+
+def test_losses_unaligned_rows(dev):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(2)
+    n, d = 999, 64
+    flat = rng.normal(size=n * d + 1)
+    X = flat[1:].reshape(n, d)
+    theta = rng.normal(size=d)
+    base = cu(flat, dev)
+    Xd = base[1:].view(n, d)                                   # 8-byte aligned only
+    l, _, _ = ops.loss(ops.LOSS_PCA, Xd, cu(theta / np.linalg.norm(theta), dev))
+    ref = rlvi_np.pca_losses(X, theta / np.linalg.norm(theta))
+    assert np.max(np.abs(l.cpu().numpy() - ref)) < 1e-11 * np.max(np.sum(X ** 2, axis=1))
+
+
+@pytest.mark.parametrize("n,d", [(50, 2), (999, 3), (2048, 16), (1500, 64), (700, 65), (300, 128)])
+def test_gaussian_loss_against_oracle(dev, n, d):
+    from rlvi_b200 import ops, utils
+    rng = np.random.default_rng(d)
+    A = rng.normal(size=(d, d)) / np.sqrt(d)
+    cov = A @ A.T + 0.5 * np.eye(d)
+    mu = rng.normal(size=d)
+    X = mu + rng.normal(size=(n, d)) @ np.linalg.cholesky(cov).T
+    ref = rlvi_np.gaussian_losses(X, mu, cov)
+    params = utils._gaussian_params(cu(mu, dev), cu(cov, dev))
+    l, _, _ = ops.loss(ops.LOSS_GAUSSIAN, cu(X, dev), params)
+    assert relmax(l.cpu().numpy(), ref) < 1e-10
+
+
+# ==================================================================================================
+# weighted M-step statistics
+# ==================================================================================================
+MOM_SHAPES = [(1, 1), (7, 2), (40, 10), (257, 31), (1000, 33), (63, 64), (64, 64), (65, 64), (4096 + 17, 64),
+              (100000, 64), (777, 65), (500, 100), (300, 512), (150, 1000)]
+
+
+@pytest.mark.parametrize("n,d", MOM_SHAPES)
+@pytest.mark.parametrize("power", [1, 2])
+def test_weighted_moments_against_oracle(dev, n, d, power):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(7 * n + d + power)
+    X = rng.normal(size=(n, d)) + 0.3
+    y = rng.normal(size=n)
+    w = rng.random(n)
+    we = w ** power
+    ref = rlvi_np.weighted_moments(X, we, y)
+    for use_y in (True, False):
+        out = ops.weighted_moments(cu(X, dev), cu(w, dev), y=cu(y, dev) if use_y else None, power=power)
+        m = {k: v.cpu().numpy() for k, v in ops.split_moments(out, d).items()}
+        assert abs(m["S0"] - ref["S0"]) < 1e-12 * ref["S0"]
+        assert relmax(m["S1"], X.T @ w) < 1e-12                 # first power always (header contract)
+        assert relmax(m["G"], ref["G"]) < 1e-12
+        assert np.array_equal(m["G"], m["G"].T)                 # exactly symmetric
+        if use_y:
+            assert relmax(m["Sy"], ref["Sy"]) < 1e-12
+            assert abs(m["Swy"] - ref["Swy"]) < 1e-12 * max(abs(ref["Swy"]), np.abs(we * y).sum() * 1e-3)
+        else:
+            assert not m["Sy"].any() and m["Swy"] == 0.0
+
+
+def test_weighted_moments_no_gram_and_determinism(dev):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(9)
+    n, d = 50000, 64
+    X, w = cu(rng.normal(size=(n, d)), dev), cu(rng.random(n), dev)
+    a = ops.weighted_moments(X, w)
+    b = ops.weighted_moments(X, w)
+    assert torch.equal(a, b)                                    # fixed-order reductions: same bits
+    c = ops.weighted_moments(X, w, want_gram=False)
+    assert torch.allclose(c[:2 + 2 * d], a[:2 + 2 * d], rtol=1e-13, atol=0)
+    assert not c[2 + 2 * d:].any()
+
+
+def test_weighted_moments_linearity_large(dev):
+    """Size-independent property at a size the oracle cannot reach quickly: moments are linear in w."""
+    from rlvi_b200 import ops
+    n, d = 1 << 21, 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.randn((n, d), generator=g, device=dev, dtype=torch.float64)
+    w1 = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    w2 = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    m1, m2, m12 = (ops.weighted_moments(X, w) for w in (w1, w2, w1 + w2))
+    scale = m12.abs().max()
+    assert float((m1 + m2 - m12).abs().max() / scale) < 1e-12
+    # and against cuBLAS on the same device (torch fp64 reference of the same contraction)
+    G = (X * (w1 + w2)[:, None]).T @ X
+    assert float((ops.split_moments(m12, d)["G"] - G).abs().max() / G.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("n,d", [(40, 10), (1031, 64), (777, 65), (300, 512)])
+def test_logistic_grad_against_oracle(dev, n, d):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d))
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    w = rng.random(n)
+    tb = rng.normal(size=d + 1) / np.sqrt(d)
+    Xa = np.hstack([np.ones((n, 1)), X])
+    ref = Xa.T @ (w * (rlvi_np.sigmoid(Xa @ tb) - y))
+    out = ops.logistic_grad(cu(X, dev), cu(y, dev), cu(w, dev), cu(tb, dev))
+    assert relmax(out.cpu().numpy(), ref) < 1e-12
+
+
+# ==================================================================================================
+# drop-in outer loops against the reference's golden outputs
+# ==================================================================================================
+@pytest.mark.parametrize("tag", ["n100_d2", "n768_d64"])
+def test_mean_golden(dev, tag):
+    from rlvi_b200 import rlvi
+    g = load_golden("mean_" + tag)
+    assert relmax(rlvi.mean(g["X"]), g["theta"]) < F64_TOL
+
+
+@pytest.mark.parametrize("tag", ["n40_d10", "n768_d64"])
+def test_linear_regression_golden(dev, tag):
+    from rlvi_b200 import rlvi
+    g = load_golden("linreg_" + tag)
+    assert relmax(rlvi.linear_regression(g["X"], g["y"]), g["theta"]) < F64_TOL
+
+
+def test_mm_log_reg_and_logistic_regression_golden(dev):
+    from rlvi_b200 import rlvi, utils
+    g = load_golden("mm_log_reg_n768_d64")
+    assert relmax(utils.sigmoid(g["x_sig"]), g["sig"]) < 1e-15
+    theta, losses = utils.mm_log_reg(g["X"], g["y"], g["w"])
+    assert relmax(theta, g["theta"]) < F64_TOL
+    assert relmax(losses, g["losses"]) < F64_TOL
+    Xa = np.hstack([np.ones((g["X"].shape[0], 1)), g["X"]])
+    assert relmax(utils.cross_entropy(Xa, g["theta"], g["y"]), g["ce_at_theta"]) < 1e-12
+    g2 = load_golden("logreg_mm_n1500_d8")
+    assert relmax(rlvi.logistic_regression(g2["X"], g2["y"], mstep="mm"), g2["theta"]) < 1e-8
+
+
+def test_sklearn_log_reg_golden(dev):
+    """liblinear is third-party and stops at tol = 1e-4: agreement is to liblinear's accuracy; the
+    in-place normalisation of the caller's weights (Q3) and the label-independent loss are exact."""
+    from rlvi_b200 import utils
+    g = load_golden("sklearn_loss_n600_d5")
+    w = g["w"].copy()
+    theta, losses = utils.sklearn_log_reg(g["X"], g["y"], w)
+    assert np.array_equal(w, g["w_after"])
+    assert relmax(theta, g["theta"]) < 5e-3
+    assert relmax(losses, rlvi_np.softplus_loss(g["X"], theta)) < 1e-12
+    assert relmax(losses, g["losses"]) < 5e-3
+
+
+@pytest.mark.parametrize("tag", ["n400_d2", "n768_d64"])
+def test_pca_golden(dev, tag):
+    from rlvi_b200 import rlvi, utils
+    g = load_golden("pca_" + tag)
+    theta, losses = utils.pca(g["X"], g["w"])
+    assert relmax(theta, g["theta_mstep"]) < 1e-8
+    assert relmax(losses, g["losses_mstep"]) < 1e-8
+    _, l0 = utils.pca(g["X"], g["w"], g["theta_init"])
+    assert relmax(l0, g["losses_init"]) < 1e-12
+    assert relmax(rlvi.pca(g["X"], theta_init=g["theta_init"]), g["theta"]) < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["n50_d2", "n2048_d16"])
+def test_covariance_golden(dev, tag):
+    from rlvi_b200 import rlvi, utils
+    g = load_golden("cov_" + tag)
+    cov, losses = utils.covariance(g["X"], g["w"])
+    assert relmax(cov, g["cov_mstep"]) < F64_TOL
+    assert relmax(losses, g["losses_mstep"]) < F64_TOL
+    out = rlvi.covariance(g["X"], float(g["eps"]))
+    assert relmax(out, g["cov"]) < 1e-5       # bounded by Brent's accuracy in the constrained E-step (H4)
+
+
+def test_covariance_singular_raises(dev):
+    from rlvi_b200 import utils
+    X = np.ones((20, 3))
+    with pytest.raises(ValueError, match="Singular covariance matrix"):
+        utils.covariance(X, np.ones(20))
+
+
+def test_cuda_tensor_in_tensor_out(dev):
+    from rlvi_b200 import rlvi
+    g = load_golden("linreg_n768_d64")
+    theta = rlvi.linear_regression(cu(g["X"], dev), cu(g["y"], dev))
+    assert isinstance(theta, torch.Tensor) and theta.is_cuda
+    assert relmax(theta.cpu().numpy(), g["theta"]) < F64_TOL
+
+
+# ==================================================================================================
+# one E+M step through the host-buffer entry point (bench.py's e2e call)
+# ==================================================================================================
+@pytest.mark.parametrize("n", [1000, 200001])
+def test_em_step_logistic_host(dev, n):
+    from rlvi_b200 import ops, synth
+    X, y, theta = synth.logistic_data(n, 64, seed=1)
+    params = np.concatenate([[0.1], theta])
+    ref = rlvi_np.em_step_logistic(X, y, params)
+    out = ops.em_step_logistic_host(X, y, params)
+    assert out["result"]["iters"] == ref["iters"]
+    assert relmax(out["pi"], ref["pi"]) < pi_tol(ref["pi"])
+    m = out["moments"]
+    d = 64
+    tol = pi_tol(ref["pi"])
+    assert abs(m[0] - ref["S0"]) < tol * ref["S0"]
+    assert relmax(m[2:2 + d], ref["S1"]) < max(tol, 1e-9) * 10
+    assert relmax(m[2 + 2 * d:].reshape(d, d), ref["G"]) < tol
+    # normalised statistics are insensitive to the collapse regime: 1e-9
+    assert relmax(m[2 + 2 * d:] / m[0], (ref["G"] / ref["S0"]).ravel()) < F64_TOL
+    assert abs(out["result"]["eps"] - ref["eps"]) <= F64_TOL
+
+
+# ==================================================================================================
+# deep path (FP32)
+# ==================================================================================================
+def test_update_sample_weights_golden(dev):
+    from rlvi_b200 import deep
+    g = load_golden("deep_estep_n45000")
+    res = cu(g["residuals"], dev)
+    w = torch.ones(res.numel(), dtype=torch.float32, device=dev)
+    deep.update_sample_weights(res, w)
+    assert relmax(res.cpu().numpy(), g["residuals_after"]) < F32_TOL
+    assert np.max(np.abs(w.cpu().numpy() - g["weights"])) < F32_TOL
+    # epoch 2 starts from the truncated weights of epoch 1 (first-pass error against INCOMING weights)
+    thr = deep.false_negative_criterion(w)
+    assert thr.dim() == 0 and abs(float(thr) - float(g["threshold"])) <= F32_TOL
+    w[w < thr] = 0
+    mask_ref = g["weights_truncated"] > 0
+    assert np.array_equal(w.cpu().numpy() > 0, mask_ref)        # identical selection mask
+    res2 = cu(g["residuals2"], dev)
+    deep.update_sample_weights(res2, w)
+    assert np.max(np.abs(w.cpu().numpy() - g["weights2"])) < F32_TOL
+    thr2 = deep.false_negative_criterion(w)
+    assert abs(float(thr2) - float(g["threshold2"])) <= F32_TOL
+
+
+def test_threshold_wrap_and_truncate(dev):
+    from rlvi_b200 import deep, ops
+    g = load_golden("deep_threshold_wrap")
+    w = cu(g["weights"], dev)
+    assert float(deep.false_negative_criterion(w)) == float(g["threshold"])     # quirk Q9
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 17, 1000, 45000, 300000):
+        wn = rng.beta(0.5, 0.5, size=n).astype(np.float32)
+        wn[rng.integers(0, n)] = 1.0
+        ref = deep_ref.false_negative_criterion(torch.from_numpy(wn))
+        wt = cu(wn, dev)
+        got = deep.false_negative_criterion(wt)
+        assert float(got) == float(ref), n
+        out = ops.fn_threshold(wt, prev_threshold=0.5, truncate=True)
+        thr = max(0.5, float(ref))
+        assert float(out) == np.float32(thr)
+        exp = wn.copy()
+        exp[exp < np.float32(thr)] = 0
+        assert np.array_equal(wt.cpu().numpy(), exp)
+
+
+def test_weighted_ce_golden_and_autograd(dev):
+    from rlvi_b200 import deep
+    g = load_golden("deep_wce_b512_c100")
+    b = g["logits"].shape[0]
+    n_train = 4 * b
+    rng = np.random.default_rng(0)
+    idx = rng.permutation(n_train)[:b].astype(np.int64)
+    weights = np.zeros(n_train, dtype=np.float32)
+    weights[idx] = g["batch_weights"]
+    logits = cu(g["logits"], dev).requires_grad_(True)
+    residuals = torch.zeros(n_train, dtype=torch.float32, device=dev)
+    loss, correct = deep.weighted_cross_entropy(logits, cu(g["labels"], dev), cu(idx, dev), cu(weights, dev),
+                                                residuals)
+    (loss * 1.0).backward()
+    assert abs(float(loss) - float(g["loss"])) < F32_TOL * abs(float(g["loss"]))
+    assert relmax(residuals.cpu().numpy()[idx], g["per_sample"]) < F32_TOL
+    assert not residuals.requires_grad                          # detached (quirk Q8)
+    assert np.max(np.abs(logits.grad.cpu().numpy() - g["dlogits"])) < F32_TOL * np.max(np.abs(g["dlogits"]))
+    # accuracy counts against torch.topk on the same logits
+    lt = torch.from_numpy(g["logits"])
+    top5 = lt.topk(5, dim=1).indices
+    lab = torch.from_numpy(g["labels"])
+    assert int(correct[0]) == int((top5[:, 0] == lab).sum())
+    assert int(correct[1]) == int((top5 == lab[:, None]).any(dim=1).sum())
+
+
+@pytest.mark.parametrize("b,c", [(1, 2), (7, 10), (100, 33), (513, 100), (64, 257), (32, 1000)])
+def test_weighted_ce_shapes(dev, b, c):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(b * c)
+    logits = torch.from_numpy((3 * rng.normal(size=(b, c))).astype(np.float32))
+    labels = torch.from_numpy(rng.integers(0, c, size=b).astype(np.int64))
+    w = torch.from_numpy(rng.random(b).astype(np.float32))
+    per, loss, dl = deep_ref.weighted_ce(logits, labels, w)
+    res = torch.zeros(b, dtype=torch.float32, device=dev)
+    r = ops.wce_fwd_bwd(logits.to(dev), labels.to(dev), w.to(dev), res, want_per_sample=True)
+    assert relmax(r["per_sample"].cpu().numpy(), per.numpy()) < F32_TOL
+    assert torch.equal(res, r["per_sample"])
+    assert abs(float(r["loss"]) - float(loss)) < F32_TOL * max(abs(float(loss)), 1e-3)
+    assert np.max(np.abs(r["dlogits"].cpu().numpy() - dl.numpy())) < F32_TOL * max(float(dl.abs().max()), 1e-6)
+
+
+def test_train_rlvi_epoch_matches_reference_restated(dev):
+    """One epoch of the drop-in `train_rlvi` against the same epoch written with the oracle's torch ops
+    on the same device (model + SGD identical): residuals, weights, accuracy and threshold agree."""
+    from rlvi_b200 import deep
+    torch.manual_seed(0)
+    n_train, c, bs = 1024, 10, 128
+    Xs = torch.randn(n_train, 20)
+    ys = torch.randint(0, c, (n_train,))
+    loader = [(Xs[i:i + bs], ys[i:i + bs], torch.arange(i, min(i + bs, n_train))) for i in range(0, n_train, bs)]
+
+    def make():
+        torch.manual_seed(1)
+        m = torch.nn.Sequential(torch.nn.Linear(20, 32), torch.nn.ReLU(), torch.nn.Linear(32, c)).to(dev)
+        return m, torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+
+    m1, o1 = make()
+    res1 = torch.zeros(n_train, device=dev)
+    w1 = torch.rand(n_train, device=dev) * 0.5 + 0.5
+    w2, res2 = w1.clone(), res1.clone()
+    acc1, thr1 = deep.train_rlvi(loader, m1, o1, res1, w1, True, 0)
+
+    m2, o2 = make()
+    correct = 0.0
+    for xb, yb, ib in loader:
+        xb, yb, ib = xb.to(dev), yb.to(dev), ib.to(dev)
+        logits = m2(xb)
+        correct += float((logits.argmax(1) == yb).float().sum() * (100.0 / yb.numel()))
+        per = torch.nn.functional.cross_entropy(logits, yb, reduction="none")
+        res2[ib] = per.detach()
+        loss = (per * w2[ib]).mean()
+        o2.zero_grad()
+        loss.backward()
+        o2.step()
+    thr2 = deep_ref.epoch_tail(res2, w2, True, 0)
+    assert abs(acc1 - correct / len(loader)) < 1e-9
+    assert torch.allclose(res1, res2, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(w1, w2, rtol=1e-4, atol=1e-5)
+    assert abs(float(thr1) - float(thr2)) < 1e-4
+    assert torch.equal(w1 > 0, w2 > 0)
