@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int kFpThreads = 256;
-constexpr int kFpUnroll = 4;            // independent 128-bit loads in flight per thread
+constexpr int kFpUnroll = 8;            // independent 128-bit loads in flight per thread
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 enum ReduceOp { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
@@ -262,32 +262,125 @@ __device__ __forceinline__ double post_f64(double e, double rho) {
   return a / (1.0 + a);
 }
 
-// pi' and (pi' - pi) with ONE division: t = 1/((rho'+e)(rho+e)).
+// 1/x for x in the normal range, to <= 1 ulp: MUFU.RCP64H seed (~2^-23) + two Newton steps (4 DFMA).
+// The IEEE division the compiler emits for `e / prod` costs ~25 instructions and a slow-path branch; the
+// fixed point evaluates it 2^26 x K times, which made the pass FP64-issue bound instead of HBM bound.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-x, r, 1.0);
+  return fma(r, t, r);
+}
+// true if 2^-900 <= |x| < 2^900 (integer test on the exponent field: keeps the FP64 pipe free)
+__device__ __forceinline__ bool in_safe_range(double x) {
+  const unsigned int ex = (unsigned int)(__double2hiint(x) >> 20) & 0x7ffu;
+  return (ex - 123u) < 1800u;
+}
+
+// pi' and (pi' - pi) with the reference's own two IEEE divisions (scalar / unaligned path, loop tails and
+// the out-of-range fallback of the fast path below).
 template <int VARIANT>
 __device__ __forceinline__ void post_pair_f64(double e, double rho_new, double rho_old, double& pnew, double& diff) {
+  pnew = post_f64<VARIANT>(e, rho_new);
+  diff = pnew - post_f64<VARIANT>(e, rho_old);
+}
+
+// The hot pass (k >= 2) over a 16-byte aligned e[]: kFpUnroll independent 128-bit loads are issued
+// before any arithmetic so that ~128 B per thread are in flight; two accumulator pairs halve the DADD/DFMA
+// dependency chains.  Loads bypass L1 (every byte is used once per pass; at <= 64 MiB per GPU the vector
+// stays L2 resident between passes).  Each thread re-reads exactly the chunks it wrote in pass 1.
+__device__ __forceinline__ double2 ld_e2(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+}
+// Branch-free fast evaluation of (pi', pi' - pi); `ok` is cleared when the operand left the safe range,
+// in which case the caller redoes the whole trip with post_pair_f64's IEEE divisions.
+template <int VARIANT>
+__device__ __forceinline__ void post_pair_fast(double e, double rho_new, double rho_old, double drho, double& pnew,
+                                               double& diff, bool& ok) {
   if (VARIANT == RLVI_FP_STANDARD) {
     const double a = rho_new + e, b = rho_old + e;
     const double prod = a * b;
-    if (prod > 1e-280 && prod < 1e280) {
-      const double t = e / prod;
-      pnew = t * b;
-      diff = t * (rho_old - rho_new);
-    } else {   // rho = inf (eps == 1, quirk Q1), e = inf/0 extremes: the reference's two divisions
-      pnew = e / a;
-      diff = pnew - e / b;
-    }
+    ok = ok && in_safe_range(prod);
+    const double t = e * rcp_fast(prod);
+    pnew = t * b;
+    diff = t * drho;                       // drho = rho_old - rho_new
   } else {
     const double a = rho_new * e, b = rho_old * e;
-    const double prod = (1.0 + a) * (1.0 + b);
-    if (prod < 1e280) {
-      const double t = 1.0 / prod;
-      pnew = a * (1.0 + b) * t;
-      diff = (a - b) * t;
-    } else {
-      pnew = a / (1.0 + a);
-      diff = pnew - b / (1.0 + b);
-    }
+    const double b1 = 1.0 + b;
+    const double prod = (1.0 + a) * b1;
+    ok = ok && in_safe_range(prod);
+    const double t = rcp_fast(prod);
+    pnew = a * b1 * t;
+    diff = (a - b) * t;
   }
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, double rho_new, double rho_old,
+                                                double& s1, double& s2) {
+  const double2* ev = reinterpret_cast<const double2*>(e);
+  const int64_t nvec = n >> 1;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const double drho = rho_old - rho_new;
+  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+    double t1a = 0.0, t1b = 0.0, t2a = 0.0, t2b = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      double pn, d;
+      post_pair_fast<VARIANT>(v[u].x, rho_new, rho_old, drho, pn, d, ok);
+      t1a += pn;
+      t2a = fma(d, d, t2a);
+      post_pair_fast<VARIANT>(v[u].y, rho_new, rho_old, drho, pn, d, ok);
+      t1b += pn;
+      t2b = fma(d, d, t2b);
+    }
+    if (!ok) {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
+      t1a = t1b = t2a = t2b = 0.0;
+#pragma unroll 1
+      for (int u = 0; u < kFpUnroll; ++u) {
+        const double2 w = ld_e2(ev + c + u * stride);   // re-load: keeps v[] in registers on the fast path
+        double pn, d;
+        post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
+        t1a += pn;
+        t2a = fma(d, d, t2a);
+        post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
+        t1b += pn;
+        t2b = fma(d, d, t2b);
+      }
+    }
+    s1a += t1a;
+    s1b += t1b;
+    s2a += t2a;
+    s2b += t2b;
+  }
+  for (; c < nvec; c += stride) {
+    const double2 v = ld_e2(ev + c);
+    double pn, d;
+    post_pair_f64<VARIANT>(v.x, rho_new, rho_old, pn, d);
+    s1a += pn;
+    s2a = fma(d, d, s2a);
+    post_pair_f64<VARIANT>(v.y, rho_new, rho_old, pn, d);
+    s1b += pn;
+    s2b = fma(d, d, s2b);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double pn, d;
+    post_pair_f64<VARIANT>(e[n - 1], rho_new, rho_old, pn, d);
+    s1a += pn;
+    s2a = fma(d, d, s2a);
+  }
+  s1 = s1a + s1b;
+  s2 = s2a + s2b;
 }
 
 // =================================================================================================
@@ -344,6 +437,8 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
           }
         }
       });
+    } else if (VEC) {
+      stream_pass_vec<VARIANT>(e, p.n, rho_new, rho_old, s1, s2);
     } else {
       for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
         const int64_t i = c * W;

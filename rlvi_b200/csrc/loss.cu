@@ -14,6 +14,7 @@
 #include <math.h>
 
 #include "rowmap.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -35,6 +36,30 @@ struct LossParams {
   double* partials;       // [grid][2]
   unsigned int* ticket;
 };
+
+// a = x.theta (or ||theta - x||^2 for SQDIST), b = x.x (PCA only), b0 = intercept, yi = label / target.
+__device__ __forceinline__ double finish_loss(int kind, double a, double b, double b0, double yi) {
+  switch (kind) {
+    case RLVI_LOSS_LOGISTIC_CE: {
+      const double phi = b0 + a;
+      return (-yi * phi + phi) + log1p(exp(-phi));          // utils.py:21, same operation order
+    }
+    case RLVI_LOSS_SOFTPLUS: {
+      const double phi = b0 + a;
+      return fmax(phi, 0.0) + log1p(exp(-fabs(phi)));        // logaddexp(0, phi)
+    }
+    case RLVI_LOSS_SQRES: {
+      const double r = yi - (b0 + a);
+      return r * r;
+    }
+    case RLVI_LOSS_SQDIST: {
+      const double r = sqrt(a);                              // np.linalg.norm(...)**2
+      return r * r;
+    }
+    default:                                                 // RLVI_LOSS_PCA
+      return b - a * a;
+  }
+}
 
 // DOTK 0: a = x.theta          (LOGISTIC_CE, SOFTPLUS, SQRES)
 // DOTK 1: a = x.theta, b = x.x (PCA)
@@ -80,34 +105,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
     a = group_sum(a, L);
     if (DOTK == 1) b = group_sum(b, L);
     if (q == 0 && valid) {
-      double loss;
-      switch (p.kind) {
-        case RLVI_LOSS_LOGISTIC_CE: {
-          const double phi = b0 + a;
-          const double yi = p.y[row];
-          loss = (-yi * phi + phi) + log1p(exp(-phi));          // utils.py:21, same operation order
-          break;
-        }
-        case RLVI_LOSS_SOFTPLUS: {
-          const double phi = b0 + a;
-          loss = fmax(phi, 0.0) + log1p(exp(-fabs(phi)));        // logaddexp(0, phi)
-          break;
-        }
-        case RLVI_LOSS_SQRES: {
-          const double r = p.y[row] - (b0 + a);
-          loss = r * r;
-          break;
-        }
-        case RLVI_LOSS_SQDIST: {
-          const double r = sqrt(a);                              // np.linalg.norm(...)**2
-          loss = r * r;
-          break;
-        }
-        default: {                                               // RLVI_LOSS_PCA
-          loss = b - a * a;
-          break;
-        }
-      }
+      const double loss = finish_loss(p.kind, a, b, b0, (p.kind == RLVI_LOSS_LOGISTIC_CE || p.kind == RLVI_LOSS_SQRES) ? p.y[row] : 0.0);
       if (p.losses) p.losses[row] = loss;
       if (p.e_out) p.e_out[row] = exp(-loss);
       if (p.w) {
@@ -127,6 +125,199 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
     }
     if (last_block_ticket(p.ticket, gridDim.x)) {
       // fixed-order final sum by warp 0 of the last block
+      if (threadIdx.x < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (unsigned int j = lane; j < gridDim.x; j += 32) {
+          a0 += p.partials[2 * j];
+          a1 += p.partials[2 * j + 1];
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+          p.wsum_out[0] = a0;
+          p.wsum_out[1] = a1;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-fed streaming kernel (d % 16 == 0, d <= 256, 16-byte aligned pointers): the headline path.
+//   * persistent, one CTA per SM: 16 consumer warps + 1 producer warp;
+//   * the producer streams 32-row tiles into an S-stage shared-memory ring: ONE cp.async.bulk (TMA engine,
+//     SASS UBLKCP) of 32*d*8 contiguous bytes of X per tile, plus 256 bytes of y and of pi, completing on
+//     an mbarrier.  (A first version issued one 512-byte copy per row into a padded pitch: the serialised
+//     per-row UBLKCP issue, ~67 clk per row, capped the kernel at 2.3 TB/s.)
+//   * tile t of the CTA is consumed by warp t mod C (C <= 16 consumer warps, each with a private ring of
+//     R stages; C*R stages fill the shared memory): lane l owns row l of the tile and does the whole
+//     d-long dot product itself.  Rows sit at their natural d*8-byte pitch (a multiple of 128 bytes), so
+//     lane l walks its row ROTATED by l 16-byte units -- unit (j + l) mod (d/2) at step j -- which makes
+//     every 128-bit shared-memory read of x and of theta bank-conflict free;
+//   * the exp / log1p tail then runs with ALL 32 lanes busy (the register-tiled kernel above leaves 3/4
+//     of the lanes idle there and exposes the global-load latency once per row group);
+//   * outputs are one coalesced 256-byte store per warp and array.
+// Algorithmic bytes per sample: d*8 (X) + 8 (y) [+ 8 (pi)] in, 8 (l) and/or 8 (e) out.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaConsumers = 16;
+constexpr int kTmaThreads = (kTmaConsumers + 1) * 32;
+constexpr int kTmaRows = 32;
+constexpr int kTmaMaxStages = 2 * kTmaConsumers;
+
+struct LossTmaParams {
+  const double* X;
+  const double* y;
+  const double* params;
+  const double* w;
+  double* losses;
+  double* e_out;
+  double* wsum_out;
+  int64_t n;
+  int d;
+  int kind;
+  int intercept;
+  int stage_bytes;    // kTmaRows * d * 8 + 512 (y, pi)
+  int ncons;          // consumer warps in use (<= kTmaConsumers)
+  int depth;          // ring stages per consumer warp; nstages = ncons * depth
+  int nstages;
+  double* partials;   // [grid][2]
+  unsigned int* ticket;
+};
+
+template <int DOTK>
+__global__ void __launch_bounds__(kTmaThreads, 1) loss_tma_kernel(const LossTmaParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = p.nstages, C = p.ncons, R = p.depth;
+  unsigned char* ring = smem_raw;
+  double* sTheta = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);      // d (+ pad to even)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sTheta + ((p.d + 1) & ~1) + 2);
+  uint64_t* empty_bar = full_bar + kTmaMaxStages;
+  double* sRed = reinterpret_cast<double*>(empty_bar + kTmaMaxStages);               // 2 * 17 doubles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = p.d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) sTheta[i] = p.params[i + (p.intercept ? 1 : 0)];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double b0 = p.intercept ? p.params[0] : 0.0;
+  const int64_t ntiles = (p.n + kTmaRows - 1) / kTmaRows;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + grid, ...   local index t -> stage t % S, warp t % 8
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const bool need_y = (p.kind == RLVI_LOSS_LOGISTIC_CE || p.kind == RLVI_LOSS_SQRES);
+  double s_wl = 0.0, s_w = 0.0;
+
+  if (warp == kTmaConsumers) {
+    // ===== producer warp =========================================================================
+    const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(d) * 8u;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      // stage ownership is static: tile t belongs to consumer warp t % C and is its (t / C)-th tile, which
+      // lives in that warp's private ring of `depth` stages.  (Letting successive uses of one stage go to
+      // different warps is unsafe: a warp could wait for phase k+1 of a barrier still in phase k, which
+      // mbarrier.try_wait.parity reports as complete.)
+      const int cw = int(t % C);
+      const int64_t r = t / C;
+      const int stage = cw * R + int(r % R);
+      const uint32_t phase = uint32_t(r / R) & 1u;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+      double* sY = reinterpret_cast<double*>(sX + tile_bytes);
+      double* sW = sY + kTmaRows;
+      const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
+      if (row0 + kTmaRows <= p.n) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + (need_y ? 256u : 0u) + (p.w ? 256u : 0u));
+          bulk_g2s(sX, p.X + row0 * d, tile_bytes, &full_bar[stage]);
+          if (need_y) bulk_g2s(sY, p.y + row0, 256, &full_bar[stage]);
+          if (p.w) bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
+        }
+      } else {
+        // ragged last tile: plain loads (rows past n are never read back by the consumer)
+        const int rows = int(p.n - row0);
+        double* sXd = reinterpret_cast<double*>(sX);
+        for (int idx = lane; idx < rows * d; idx += 32) sXd[idx] = p.X[row0 * d + idx];
+        if (lane < rows) {
+          sY[lane] = need_y ? p.y[row0 + lane] : 0.0;
+          sW[lane] = p.w ? p.w[row0 + lane] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+      }
+    }
+  } else if (warp < C) {
+    // ===== consumer warps ========================================================================
+    const double2* th2 = reinterpret_cast<const double2*>(sTheta);
+    const int npair = d >> 1;                      // 16-byte units per row, a multiple of 8
+    const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(d) * 8u;
+    for (int64_t t = warp; t < my_tiles; t += C) {
+      const int64_t r = t / C;
+      const int stage = warp * R + int(r % R);
+      const uint32_t phase = uint32_t(r / R) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+      const double* sY = reinterpret_cast<const double*>(sX + tile_bytes);
+      const double* sW = sY + kTmaRows;
+      const double2* xr = reinterpret_cast<const double2*>(sX) + size_t(lane) * npair;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, q0 = 0.0, q1 = 0.0;
+      int u = lane % npair;                         // rotated walk: conflict-free at the natural pitch
+#pragma unroll 4
+      for (int j = 0; j < npair; j += 2) {
+        int u1 = u + 1;
+        if (u1 == npair) u1 = 0;
+        const double2 x0 = xr[u], x1 = xr[u1];
+        const double2 t0 = th2[u], t1 = th2[u1];
+        u = u1 + 1;
+        if (u == npair) u = 0;
+        if (DOTK == 2) {
+          const double v0 = t0.x - x0.x, v1 = t0.y - x0.y, v2 = t1.x - x1.x, v3 = t1.y - x1.y;
+          a0 = fma(v0, v0, a0);
+          a1 = fma(v1, v1, a1);
+          a2 = fma(v2, v2, a2);
+          a3 = fma(v3, v3, a3);
+        } else {
+          a0 = fma(x0.x, t0.x, a0);
+          a1 = fma(x0.y, t0.y, a1);
+          a2 = fma(x1.x, t1.x, a2);
+          a3 = fma(x1.y, t1.y, a3);
+          if (DOTK == 1) {
+            q0 = fma(x0.x, x0.x, q0);
+            q1 = fma(x0.y, x0.y, q1);
+            q0 = fma(x1.x, x1.x, q0);
+            q1 = fma(x1.y, x1.y, q1);
+          }
+        }
+      }
+      const double a = (a0 + a1) + (a2 + a3);
+      const double b = q0 + q1;
+      const double yi = sY[lane];
+      const double wi = sW[lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);      // the stage can be refilled while we do the tail
+      const int64_t row = (blockIdx.x + t * gridDim.x) * kTmaRows + lane;
+      if (row < p.n) {
+        const double loss = finish_loss(p.kind, a, b, b0, need_y ? yi : 0.0);
+        if (p.losses) p.losses[row] = loss;
+        if (p.e_out) p.e_out[row] = exp(-loss);
+        if (p.w) {
+          s_wl = fma(wi, loss, s_wl);
+          s_w += wi;
+        }
+      }
+    }
+  }
+
+  if (p.w) {   // uniform across the grid
+    double v[2] = {s_wl, s_w};
+    block_sum<2>(v, sRed);
+    if (threadIdx.x == 0) {
+      p.partials[2 * blockIdx.x] = v[0];
+      p.partials[2 * blockIdx.x + 1] = v[1];
+    }
+    if (last_block_ticket(p.ticket, gridDim.x)) {
       if (threadIdx.x < 32) {
         double a0 = 0.0, a1 = 0.0;
         for (unsigned int j = lane; j < gridDim.x; j += 32) {
@@ -166,12 +357,6 @@ struct GaussParams {
   double* partials;
   unsigned int* ticket;
 };
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
 
 template <int NB_MAX, bool VEC>
 __global__ void __launch_bounds__(kLossThreads) gaussian_loss_kernel(const GaussParams p) {
@@ -350,6 +535,52 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
     RLVI_GAUSS_CASE(16, false)
 #undef RLVI_GAUSS_CASE
     return RLVI_ERR_UNSUPPORTED;
+  }
+
+  // ---- TMA-fed path: d % 16 == 0, <= 256, all streamed arrays 16-byte aligned, at least one full tile ----
+  if (d % 16 == 0 && d <= 256 && n >= kTmaRows && rlvi_aligned16(X) && (!y || rlvi_aligned16(y)) &&
+      (!weights || rlvi_aligned16(weights))) {
+    LossTmaParams q;
+    q.X = X;
+    q.y = y;
+    q.params = params;
+    q.w = weights;
+    q.losses = losses_out;
+    q.e_out = e_out;
+    q.wsum_out = wsum_out;
+    q.n = n;
+    q.d = d;
+    q.kind = kind;
+    q.intercept = intercept ? 1 : 0;
+    q.stage_bytes = kTmaRows * d * 8 + 512;
+    const size_t tail = size_t(((d + 1) & ~1) + 2) * 8 + 2 * kTmaMaxStages * 8 + 2 * (kTmaConsumers + 1) * 8 + 128;
+    const int max_stages = int((size_t(220) * 1024 - tail) / q.stage_bytes);
+    q.ncons = max_stages < kTmaConsumers ? max_stages : kTmaConsumers;
+    q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
+    if (q.depth > 2) q.depth = 2;
+    const int stages = q.ncons * q.depth;
+    const int64_t ntiles = (n + kTmaRows - 1) / kTmaRows;
+    if (stages >= 2) {
+      q.nstages = stages;
+      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
+      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+      int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * 2 * sizeof(double), &scratch);
+      if (rc != RLVI_OK) return rc;
+      q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
+      q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
+      const size_t smem = size_t(stages) * q.stage_bytes + tail;
+#define RLVI_TMA_CASE(K)                                                                                   \
+  {                                                                                                        \
+    RLVI_CUDA(cudaFuncSetAttribute(loss_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    loss_tma_kernel<K><<<grid, kTmaThreads, smem, st>>>(q);                                                \
+    RLVI_LAUNCH_CHECK(ctx);                                                                                \
+    return RLVI_OK;                                                                                        \
+  }
+      if (kind == RLVI_LOSS_PCA) RLVI_TMA_CASE(1)
+      if (kind == RLVI_LOSS_SQDIST) RLVI_TMA_CASE(2)
+      RLVI_TMA_CASE(0)
+#undef RLVI_TMA_CASE
+    }
   }
 
   RowMapCfg cfg;

@@ -9,9 +9,9 @@
 //
 // d == 64 fast path (the headline shape, N = 2^26):
 //   * persistent kernel, one CTA per SM, 8 consumer warps + 1 producer warp;
-//   * the producer streams 64-row tiles (32 KiB of X + the rows' w and y) into a 5-stage shared-memory
-//     ring with cp.async.bulk (the TMA engine; SASS UBLKCP) completing on mbarriers -- one 512-byte copy
-//     per row into a 528-byte pitch so that the consumers' 128-bit fragment reads are bank-conflict free;
+//   * the producer streams 64-row tiles (32 KiB of X + the rows' w and y) into a 6-stage shared-memory
+//     ring with cp.async.bulk (the TMA engine; SASS UBLKCP) completing on mbarriers -- one contiguous
+//     32 KiB copy per tile (per-row copies into a padded pitch were issue-bound, see the producer loop);
 //   * each consumer warp takes 4-sample k-groups and issues mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the
 //     only FP64 tensor shape sm_100a has; tcgen05 has no f64 kind) for the 36 upper-triangular 8x8
 //     tiles of G, A = w * x (row scaling done in registers), B = x; all 72 accumulators of a lane stay
@@ -26,57 +26,18 @@
 #include <math.h>
 
 #include "rowmap.cuh"
+#include "tma.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier + bulk async copy (TMA engine, 1-D form)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
 
 // ---------------------------------------------------------------------------------------------
 // d = 64 fast path
 // ---------------------------------------------------------------------------------------------
 constexpr int kD = 64;
 constexpr int kTileRows = 64;
-constexpr int kPitchBytes = 528;                      // 512 + 16: rows land 16 B further round the banks
+constexpr int kPitchBytes = 512;                      // natural pitch: one contiguous TMA copy per tile
 constexpr int kPitchD = kPitchBytes / 8;              // 66 doubles
-constexpr int kStages = 5;
+constexpr int kStages = 6;
 constexpr int kConsumers = 8;                         // consumer warps
 constexpr int kGramThreads = 384;                    // 2 consumer warpgroups + 1 producer warpgroup (1 active warp)
 constexpr int kStageBytes = kTileRows * kPitchBytes + 2 * kTileRows * 8;   // X tile + w + y
@@ -133,15 +94,15 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
         double* sY = sW + kTileRows;
         const int64_t row0 = tile * kTileRows;
         if (row0 + kTileRows <= p.n) {
-          if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], kTileRows * 512 + 512 + (HAS_Y ? 512 : 0));
-          __syncwarp();
-#pragma unroll
-          for (int rr = 0; rr < kTileRows / 32; ++rr) {
-            const int r = lane + 32 * rr;
-            bulk_g2s(sX + r * kPitchBytes, p.X + (row0 + r) * kD, 512, &full_bar[stage]);
+          // ONE 32 KiB copy per tile.  (Per-row 512-byte copies into a padded pitch made the fragment reads
+          // conflict free but the serialised UBLKCP issue, ~60 clk per row, left the tensor pipe 40 % idle;
+          // the 4-way conflicts of the natural pitch cost 64 LSU clk per 144 DMMA clk and are hidden.)
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], kTileRows * 512 + 512 + (HAS_Y ? 512 : 0));
+            bulk_g2s(sX, p.X + row0 * kD, kTileRows * 512, &full_bar[stage]);
+            bulk_g2s(sW, p.w + row0, 512, &full_bar[stage]);
+            if (HAS_Y) bulk_g2s(sY, p.y + row0, 512, &full_bar[stage]);
           }
-          if (lane == 0) bulk_g2s(sW, p.w + row0, 512, &full_bar[stage]);
-          if (HAS_Y && lane == 1) bulk_g2s(sY, p.y + row0, 512, &full_bar[stage]);
         } else {
           // ragged last tile: plain loads, zero fill (w = 0 and x = 0 => no contribution)
           double* sXd = reinterpret_cast<double*>(sX);
@@ -184,7 +145,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
       const unsigned char* sX = smem + stage * kStageBytes;
       const double* sW = reinterpret_cast<const double*>(sX + kTileRows * kPitchBytes);
       const double* sY = sW + kTileRows;
-#pragma unroll 1
+#pragma unroll
       for (int kk = 0; kk < kTileRows / (4 * kConsumers); ++kk) {
         const int r = (warp + kConsumers * kk) * 4 + t;
         const unsigned char* xr = sX + r * kPitchBytes + cidx * 16;
@@ -206,13 +167,17 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
           s1[j] = fma(w1, b[j], s1[j]);
           if (HAS_Y) sy[j] = fma(wy, b[j], sy[j]);
         }
+        // all eight scaled A fragments first (one register each): with a single temporary the DMUL ->
+        // DMMA -> DMUL chain serialised the tensor pipe (ncu: 60 % DMMA utilisation, stall_math on DMUL)
+        double a[8];
+#pragma unroll
+        for (int I = 0; I < 8; ++I) a[I] = we * b[I];
         int idx = 0;
 #pragma unroll
         for (int I = 0; I < 8; ++I) {
-          const double a = we * b[I];
 #pragma unroll
           for (int J = I; J < 8; ++J) {
-            dmma884(acc[2 * idx], acc[2 * idx + 1], a, b[J]);
+            dmma884(acc[2 * idx], acc[2 * idx + 1], a[I], b[J]);
             ++idx;
           }
         }

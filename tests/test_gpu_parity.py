@@ -204,6 +204,27 @@ def test_losses_against_oracle(dev, n, d):
     assert np.max(np.abs(l6.cpu().numpy() - refp)) < 1e-12 * np.max(np.sum(X ** 2, axis=1))
 
 
+@pytest.mark.parametrize("n,d", [(300001, 64), (150000, 16), (70001, 128), (20000, 256)])
+def test_losses_many_tiles_per_cta(dev, n, d):
+    """TMA path with several ring rounds per consumer warp (n >> 148 SMs x 16 warps x 32 rows) and a ragged tail."""
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d))
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    w = rng.random(n)
+    tb = np.concatenate([[0.2], rng.normal(size=d) / np.sqrt(d)])
+    ref = rlvi_np.cross_entropy(np.hstack([np.ones((n, 1)), X]), tb, y)
+    for rep in range(2):
+        l, e, ws = ops.loss(ops.LOSS_LOGISTIC_CE, cu(X, dev), cu(tb, dev), y=cu(y, dev), intercept=True,
+                            weights=cu(w, dev), want_e=True)
+        assert relmax(l.cpu().numpy(), ref) < 1e-12
+        assert relmax(e.cpu().numpy(), np.exp(-ref)) < 1e-12
+        assert abs(ws[0].item() - w @ ref) < 1e-12 * abs(w @ ref)
+    v = tb[1:] / np.linalg.norm(tb[1:])
+    l6, _, _ = ops.loss(ops.LOSS_PCA, cu(X, dev), cu(v, dev))
+    assert np.max(np.abs(l6.cpu().numpy() - rlvi_np.pca_losses(X, v))) < 1e-12 * np.max(np.sum(X ** 2, axis=1))
+
+
 def test_losses_unaligned_rows(dev):
     from rlvi_b200 import ops
     rng = np.random.default_rng(2)
