@@ -36,7 +36,7 @@ UNIT = "samples/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=26, help="total samples = 2^log2n (default: the named config)")
@@ -125,6 +125,14 @@ def cpu_em_step_bench(log2n, d, steps, warmup):
                       f"{iters} fixed-point passes; BLAS threads={blas_threads}, os.cpu_count()={os.cpu_count()}"}, dt
 
 
+def workload_config(args, world):
+    """The `config` both arms report (BASELINE.json configs[1])."""
+    return {"workload": f"logistic E+M step (loss pass + epsilon fixed point tol 1e-3 + pi-weighted X^T Pi X), "
+                        f"N=2^{args.log2n} samples x d={args.d} FP64, 30% label corruption",
+            "n_total": 1 << args.log2n, "d": args.d, "fixed_point_tol": 1e-3, "fixed_point_maxiter": 100,
+            "parallelism": f"sample-sharded dp{world}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,8 +143,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"logistic E+M step, CPU sample N=2^{args.cpu_log2n}, d={args.d}, 30% label corruption "
-                                   f"(bounded sample of the N=2^{args.log2n} workload)"},
+            "config": dict(workload_config(args, args.gpus),
+                           sample=f"each step runs a bounded sample: N=2^{args.cpu_log2n} rows of the same workload"),
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -236,7 +244,7 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
-                "step_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak * (world if world > 1 else 1),
+                "step_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak,   # per GPU
                 "kernels": kernels}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
@@ -248,12 +256,8 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"logistic E+M step (loss pass + epsilon fixed point + pi-weighted X^T Pi X), "
-                                   f"N=2^{args.log2n} samples x d={d} FP64, 30% label corruption, sample-sharded over "
-                                   f"{world} GPU(s)",
-                       "n_total": n_total, "d": d, "fixed_point_passes": k_fp, "fixed_point_tol": 1e-3,
-                       "l2": "inputs larger than L2 (X shard %.1f GiB streamed twice per step)" % (n * d * 8 / 2 ** 30),
-                       "parallelism": f"sample-sharded dp{world}"},
+            "config": dict(workload_config(args, world), fixed_point_passes=k_fp,
+                           l2="inputs larger than L2 (X shard %.1f GiB streamed twice per step)" % (n * d * 8 / 2 ** 30)),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")}}
 

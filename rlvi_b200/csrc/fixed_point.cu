@@ -383,6 +383,71 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, doub
   s2 = s2a + s2b;
 }
 
+// Pass 1 over a precomputed, 16-byte aligned e[] (the loss kernel wrote it): pi' against the constant
+// initial posterior, plus max e (ONLINE's normalisation).  Same load batching as stream_pass_vec.
+template <int VARIANT>
+__device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, double rho, double pi0, double& s1,
+                                               double& s2, double& mx) {
+  const double2* ev = reinterpret_cast<const double2*>(e);
+  const int64_t nvec = n >> 1;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0, m = 0.0;
+  auto one = [&](double x, double& sa, double& sb) {
+    const double pn = post_f64<VARIANT>(x, rho);
+    const double d = pn - pi0;
+    sa += pn;
+    sb = fma(d, d, sb);
+    m = fmax(m, x);
+  };
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      one(v[u].x, s1a, s2a);
+      one(v[u].y, s1b, s2b);
+    }
+  }
+  for (; c < nvec; c += stride) {
+    const double2 v = ld_e2(ev + c);
+    one(v.x, s1a, s2a);
+    one(v.y, s1b, s2b);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) one(e[n - 1], s1a, s2a);
+  s1 = s1a + s1b;
+  s2 = s2a + s2b;
+  mx = m;
+}
+
+// Final pass: pi = the reference's own expression (IEEE division), optionally divided by `norm` (ONLINE).
+template <int VARIANT>
+__device__ __forceinline__ void final_pass_vec(const double* e, double* out, int64_t n, double rho, double norm) {
+  const double2* ev = reinterpret_cast<const double2*>(e);
+  double2* ov = reinterpret_cast<double2*>(out);
+  const int64_t nvec = n >> 1;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto one = [&](double x) {
+    double pv = post_f64<VARIANT>(x, rho);
+    if (VARIANT == RLVI_FP_ONLINE) pv = pv / norm;
+    return pv;
+  };
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) ov[c + u * stride] = make_double2(one(v[u].x), one(v[u].y));
+  }
+  for (; c < nvec; c += stride) {
+    const double2 v = ld_e2(ev + c);
+    ov[c] = make_double2(one(v.x), one(v.y));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = one(e[n - 1]);
+}
+
 // =================================================================================================
 // FP64 kernel: STANDARD and ONLINE
 // =================================================================================================
@@ -413,7 +478,9 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   bool ok = true;
   for (;; ++k) {
     double s1 = 0.0, s2 = 0.0, mx = 0.0;
-    if (k == 1) {
+    if (k == 1 && VEC && !have_losses) {
+      first_pass_vec<VARIANT>(e, p.n, rho_new, pi0, s1, s2, mx);
+    } else if (k == 1) {
       for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
         const int64_t i = c * W;
         double ev[W];
@@ -484,7 +551,9 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   // division), then the variant's normalisation
   double norm = 1.0;
   if (VARIANT == RLVI_FP_ONLINE) norm = post_f64<VARIANT>(emax, rho_new) * n_glob;   // max(pi') * n
-  if (ok) {
+  if (ok && VEC) {
+    final_pass_vec<VARIANT>(e, p.pi_out, p.n, rho_new, norm);
+  } else if (ok) {
     double* out = p.pi_out;
     for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
       const int64_t i = c * W;

@@ -213,39 +213,38 @@ __global__ void __launch_bounds__(kTmaThreads, 1) loss_tma_kernel(const LossTmaP
 
   if (warp == kTmaConsumers) {
     // ===== producer warp =========================================================================
+    // Lane c of the producer warp feeds consumer warp c (its private ring of R stages), so a slow consumer
+    // never blocks the refills of the others.  Stage ownership is static: the r-th tile of consumer c is
+    // local tile c + r C and lives in stage c R + r % R.  (Letting successive uses of one stage go to
+    // different warps is unsafe: a warp could wait for phase k+1 of a barrier still in phase k, which
+    // mbarrier.try_wait.parity reports as complete.)
     const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(d) * 8u;
-    for (int64_t t = 0; t < my_tiles; ++t) {
-      // stage ownership is static: tile t belongs to consumer warp t % C and is its (t / C)-th tile, which
-      // lives in that warp's private ring of `depth` stages.  (Letting successive uses of one stage go to
-      // different warps is unsafe: a warp could wait for phase k+1 of a barrier still in phase k, which
-      // mbarrier.try_wait.parity reports as complete.)
-      const int cw = int(t % C);
-      const int64_t r = t / C;
-      const int stage = cw * R + int(r % R);
-      const uint32_t phase = uint32_t(r / R) & 1u;
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
-      unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-      double* sY = reinterpret_cast<double*>(sX + tile_bytes);
-      double* sW = sY + kTmaRows;
-      const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
-      if (row0 + kTmaRows <= p.n) {
-        if (lane == 0) {
+    if (lane < C) {
+      int64_t r = 0;
+      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
+        const int stage = lane * R + int(r % R);
+        const uint32_t phase = uint32_t(r / R) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+        double* sY = reinterpret_cast<double*>(sX + tile_bytes);
+        double* sW = sY + kTmaRows;
+        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
+        if (row0 + kTmaRows <= p.n) {
           mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + (need_y ? 256u : 0u) + (p.w ? 256u : 0u));
           bulk_g2s(sX, p.X + row0 * d, tile_bytes, &full_bar[stage]);
           if (need_y) bulk_g2s(sY, p.y + row0, 256, &full_bar[stage]);
           if (p.w) bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
+        } else {
+          // ragged last tile: X rows by one (shorter) bulk copy, y / pi by plain stores that the
+          // release semantics of the arrive below publish (rows past n are never read back)
+          const int rows = int(p.n - row0);
+          for (int i = 0; i < rows; ++i) {
+            sY[i] = need_y ? p.y[row0 + i] : 0.0;
+            sW[i] = p.w ? p.w[row0 + i] : 0.0;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(d) * 8u);
+          bulk_g2s(sX, p.X + row0 * d, uint32_t(rows) * uint32_t(d) * 8u, &full_bar[stage]);
         }
-      } else {
-        // ragged last tile: plain loads (rows past n are never read back by the consumer)
-        const int rows = int(p.n - row0);
-        double* sXd = reinterpret_cast<double*>(sX);
-        for (int idx = lane; idx < rows * d; idx += 32) sXd[idx] = p.X[row0 * d + idx];
-        if (lane < rows) {
-          sY[lane] = need_y ? p.y[row0 + lane] : 0.0;
-          sW[lane] = p.w ? p.w[row0 + lane] : 0.0;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
       }
     }
   } else if (warp < C) {

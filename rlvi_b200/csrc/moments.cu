@@ -10,8 +10,8 @@
 // d == 64 fast path (the headline shape, N = 2^26):
 //   * persistent kernel, one CTA per SM, 8 consumer warps + 1 producer warp;
 //   * the producer streams 64-row tiles (32 KiB of X + the rows' w and y) into a 6-stage shared-memory
-//     ring with cp.async.bulk (the TMA engine; SASS UBLKCP) completing on mbarriers -- one contiguous
-//     32 KiB copy per tile (per-row copies into a padded pitch were issue-bound, see the producer loop);
+//     ring with cp.async.bulk (the TMA engine; SASS UBLKCP) completing on mbarriers -- four 8 KiB copies
+//     per tile, skewed by 16 bytes each so that the fragment reads are bank-conflict free;
 //   * each consumer warp takes 4-sample k-groups and issues mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the
 //     only FP64 tensor shape sm_100a has; tcgen05 has no f64 kind) for the 36 upper-triangular 8x8
 //     tiles of G, A = w * x (row scaling done in registers), B = x; all 72 accumulators of a lane stay
@@ -35,12 +35,13 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 constexpr int kD = 64;
 constexpr int kTileRows = 64;
-constexpr int kPitchBytes = 512;                      // natural pitch: one contiguous TMA copy per tile
-constexpr int kPitchD = kPitchBytes / 8;              // 66 doubles
+constexpr int kGroupRows = 16;                        // rows per TMA copy; a tile = 4 groups
+constexpr int kGroupPitch = kGroupRows * 512 + 16;    // groups land 16 B further round the banks (see consumer)
 constexpr int kStages = 6;
 constexpr int kConsumers = 8;                         // consumer warps
 constexpr int kGramThreads = 384;                    // 2 consumer warpgroups + 1 producer warpgroup (1 active warp)
-constexpr int kStageBytes = kTileRows * kPitchBytes + 2 * kTileRows * 8;   // X tile + w + y
+constexpr int kXBytes = 4 * kGroupPitch;              // 32832
+constexpr int kStageBytes = ((kXBytes + 2 * kTileRows * 8) + 127) / 128 * 128;   // X tile + w + y
 constexpr int kTiles36 = 36;
 constexpr int kCompact = kTiles36 * 64;               // 2304 doubles: 36 tiles of 8x8
 constexpr int kPartialStride = 2 + 2 * kD + kCompact; // S0, Swy, S1, Sy, G(compact)
@@ -90,25 +91,29 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         unsigned char* sX = smem + stage * kStageBytes;
-        double* sW = reinterpret_cast<double*>(sX + kTileRows * kPitchBytes);
+        double* sW = reinterpret_cast<double*>(sX + kXBytes);
         double* sY = sW + kTileRows;
         const int64_t row0 = tile * kTileRows;
         if (row0 + kTileRows <= p.n) {
-          // ONE 32 KiB copy per tile.  (Per-row 512-byte copies into a padded pitch made the fragment reads
-          // conflict free but the serialised UBLKCP issue, ~60 clk per row, left the tensor pipe 40 % idle;
-          // the 4-way conflicts of the natural pitch cost 64 LSU clk per 144 DMMA clk and are hidden.)
+          // FOUR 8 KiB copies per tile, one per 16-row group, each landing 16 bytes further round the banks.
+          // (Per-row 512-byte copies into a padded pitch made the fragment reads conflict free but the
+          // serialised UBLKCP issue, ~60 clk per row, left the tensor pipe 40 % idle.)  The four k-slots of
+          // one DMMA take one row from EACH group, so the 16-byte skew between groups is what separates the
+          // banks of the four rows a quarter-warp reads together.
           if (lane == 0) {
             mbar_arrive_expect_tx(&full_bar[stage], kTileRows * 512 + 512 + (HAS_Y ? 512 : 0));
-            bulk_g2s(sX, p.X + row0 * kD, kTileRows * 512, &full_bar[stage]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              bulk_g2s(sX + q * kGroupPitch, p.X + (row0 + q * kGroupRows) * kD, kGroupRows * 512, &full_bar[stage]);
             bulk_g2s(sW, p.w + row0, 512, &full_bar[stage]);
             if (HAS_Y) bulk_g2s(sY, p.y + row0, 512, &full_bar[stage]);
           }
         } else {
           // ragged last tile: plain loads, zero fill (w = 0 and x = 0 => no contribution)
-          double* sXd = reinterpret_cast<double*>(sX);
           for (int idx = lane; idx < kTileRows * kD; idx += 32) {
             const int r = idx >> 6, c = idx & 63;
-            sXd[r * kPitchD + c] = (row0 + r < p.n) ? p.X[(row0 + r) * kD + c] : 0.0;
+            double* dst = reinterpret_cast<double*>(sX + (r / kGroupRows) * kGroupPitch + (r % kGroupRows) * 512);
+            dst[c] = (row0 + r < p.n) ? p.X[(row0 + r) * kD + c] : 0.0;
           }
           for (int r = lane; r < kTileRows; r += 32) {
             sW[r] = (row0 + r < p.n) ? p.w[row0 + r] : 0.0;
@@ -143,12 +148,14 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       mbar_wait(&full_bar[stage], phase);
       const unsigned char* sX = smem + stage * kStageBytes;
-      const double* sW = reinterpret_cast<const double*>(sX + kTileRows * kPitchBytes);
+      const double* sW = reinterpret_cast<const double*>(sX + kXBytes);
       const double* sY = sW + kTileRows;
 #pragma unroll
       for (int kk = 0; kk < kTileRows / (4 * kConsumers); ++kk) {
-        const int r = (warp + kConsumers * kk) * 4 + t;
-        const unsigned char* xr = sX + r * kPitchBytes + cidx * 16;
+        // k-group kg = warp + 8 kk: its four samples are row kg of each 16-row group (k-slot t <-> group t)
+        const int kg = warp + kConsumers * kk;
+        const int r = t * kGroupRows + kg;
+        const unsigned char* xr = sX + t * kGroupPitch + kg * 512 + cidx * 16;
         const double2 x0 = *reinterpret_cast<const double2*>(xr);
         const double2 x1 = *reinterpret_cast<const double2*>(xr + 128);
         const double2 x2 = *reinterpret_cast<const double2*>(xr + 256);

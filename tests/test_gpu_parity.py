@@ -293,7 +293,8 @@ def test_weighted_moments_no_gram_and_determinism(dev):
     b = ops.weighted_moments(X, w)
     assert torch.equal(a, b)                                    # fixed-order reductions: same bits
     c = ops.weighted_moments(X, w, want_gram=False)
-    assert torch.allclose(c[:2 + 2 * d], a[:2 + 2 * d], rtol=1e-13, atol=0)
+    # different kernels, different (fixed) summation orders: agreement relative to the largest entry
+    assert float((c[:2 + 2 * d] - a[:2 + 2 * d]).abs().max() / a[:2 + 2 * d].abs().max()) < 1e-13
     assert not c[2 + 2 * d:].any()
 
 
