@@ -213,6 +213,11 @@ def run_b200(args):
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     sampler.start()
+    if world > 1:
+        # align the ranks on the GPU timeline: the CPUs leave the barrier above milliseconds apart, and a rank
+        # that starts early would only spin in its first sharded fixed-point pass waiting for the others
+        align = torch.zeros(1, device=dev)
+        torch.distributed.all_reduce(align)
     t_begin.record()
     for k in range(args.steps):
         step(k)
@@ -230,6 +235,7 @@ def run_b200(args):
 
     # per-kernel averages (this rank) and the roofline of the dominant kernel
     kms = np.array([[ev[k][i].elapsed_time(ev[k][i + 1]) for i in range(3)] for k in range(args.steps)]).mean(axis=0)
+    gaps = [ev[k][3].elapsed_time(ev[k + 1][0]) for k in range(args.steps - 1)]
     k_fp = fp["iters"]
     alg_bytes = {"loss_kernel": n * (d * 8 + 8 + 8), "fp_kernel_f64": n * 8 * (k_fp + 1) + n * 8,
                  "gram64_kernel": n * (d * 8 + 8)}
@@ -259,7 +265,8 @@ def run_b200(args):
             "config": dict(workload_config(args, world), fixed_point_passes=k_fp,
                            l2="inputs larger than L2 (X shard %.1f GiB streamed twice per step)" % (n * d * 8 / 2 ** 30)),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")}}
+            "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")},
+            "host": {"cpus": os.cpu_count(), "inter_step_gap_ms": float(np.mean(gaps)) if gaps else 0.0}}
 
     # ---- e2e: the same step through the host-buffer C-ABI call, H2D/D2H inside the timed region --------
     if not args.no_e2e:

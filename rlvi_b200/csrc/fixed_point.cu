@@ -77,11 +77,17 @@ struct FpShared {
   double warp_part[3 * (kFpThreads / 32)];
   double total[3];
   int failed;
+  int is_last;
 };
 
-// Grid-wide (and, with dist, cross-GPU) reduction of three values; v2 uses OP2.  On return all
-// threads of all blocks (of all ranks) hold the same totals.  `round` counts reduction rounds and is
-// advanced here.  Returns false if a wait timed out (a peer died / launch was not co-resident).
+// Grid-wide (and, with dist, cross-GPU) reduction of three values; v2 uses OP2.  On return all threads
+// of all blocks (of all ranks) hold the same totals.  `round` counts reduction rounds and is advanced here.
+// Returns false if a wait timed out (a peer died / launch was not co-resident).
+//
+// One hop: every block stores its partial and takes a ticket; the LAST block to arrive sums the partials in
+// block order and PUBLISHES the rank's totals + a sequence tag -- into slot `rank` of every rank's window
+// (over NVLink for the peers; world == 1 uses a local window in the context scratch).  All blocks then poll
+// their own window for the `world` tags, which doubles as the grid barrier, and add the slots in rank order.
 template <typename T, int OP2>
 __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, double& v1, double& v2,
                                 unsigned int& round) {
@@ -111,74 +117,64 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     mine[0] = a;
     mine[1] = b;
     mine[2] = c;
-    // ---- grid barrier (cooperative launch guarantees co-residency)
     __threadfence();
-    atomicAdd(p.control, 1u);
-    const unsigned int target = (round + 1u) * gridDim.x;
-    const unsigned long long t0 = gtime_ns();
-    int failed = 0;
-    while (ld_acquire_u32(p.control) < target) {
-      if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
-      if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
-    }
-    __threadfence();
-    sh.failed = failed;
+    const unsigned int ticket = atomicAdd(p.control, 1u);
+    sh.is_last = (ticket == (round + 1u) * gridDim.x - 1u) ? 1 : 0;
+    if (sh.is_last) __threadfence();
   }
   __syncthreads();
-  if (sh.failed) return false;
-  // ---- every block sums all block partials in the same order (lane-strided, then xor tree)
+  // Tag and window slot: two windows per call parity and two per round parity, so a fast rank that already
+  // started the NEXT round / call can never overwrite a slot a slow rank has not read yet (a rank can be at
+  // most one published round ahead of any peer).
+  const unsigned long long tag = (p.call_index << 20) + round + 1ull;
+  const size_t slot = (size_t(((p.call_index & 1ull) << 1) | buf) * p.world) * 4;
   if (warp == 0) {
-    const double* all = p.partials + size_t(buf) * gridDim.x * 4;
-    double a = 0.0, b = 0.0;
-    double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
-    for (unsigned int j = lane; j < gridDim.x; j += 32) {
-      a += ld_volatile_f64(all + j * 4 + 0);
-      b += ld_volatile_f64(all + j * 4 + 1);
-      const double t = ld_volatile_f64(all + j * 4 + 2);
-      c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    c = (OP2 == OP_SUM) ? warp_sum(c) : (OP2 == OP_MIN ? warp_min(c) : warp_max(c));
-    int failed = 0;
-    if (p.world > 1) {
-      // ---- cross-GPU stage: publish this rank's totals, then sum all ranks' in rank order
-      // Tag and window slot: two windows per call parity, so a fast rank that already started the
-      // NEXT call can never overwrite a slot a slow rank has not read yet (a rank can be at most one
-      // published round ahead of any peer).
-      const unsigned long long tag = (p.call_index << 20) + round + 1ull;
-      const size_t slot = (size_t(((p.call_index & 1ull) << 1) | buf) * p.world) * 4;
-      if (blockIdx.x == 0 && lane < p.world) {
-        double* dst = p.peer_inbox[lane] + slot + size_t(p.rank) * 4;
+    if (sh.is_last) {
+      // ---- the last block sums all block partials in block order (lane-strided, then xor tree) ...
+      const double* all = p.partials + size_t(buf) * gridDim.x * 4;
+      double a = 0.0, b = 0.0;
+      double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
+      for (unsigned int j = lane; j < gridDim.x; j += 32) {
+        a += ld_volatile_f64(all + j * 4 + 0);
+        b += ld_volatile_f64(all + j * 4 + 1);
+        const double t = ld_volatile_f64(all + j * 4 + 2);
+        c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      c = (OP2 == OP_SUM) ? warp_sum(c) : (OP2 == OP_MIN ? warp_min(c) : warp_max(c));
+      // ---- ... and publishes them to every rank's window (lane r -> rank r)
+      if (lane < p.world) {
+        double* dst = (p.world > 1 ? p.peer_inbox[lane] : p.inbox) + slot + size_t(p.rank) * 4;
         dst[0] = a;
         dst[1] = b;
         dst[2] = c;
         __threadfence_system();
         st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
       }
-      double ra = 0.0, rb = 0.0, rc = 0.0;
-      if (lane < p.world) {
-        const double* src = p.inbox + slot + size_t(lane) * 4;
-        const unsigned long long t0 = gtime_ns();
-        while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != tag) {
-          if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
-          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
-        }
-        ra = ld_volatile_f64(src + 0);
-        rb = ld_volatile_f64(src + 1);
-        rc = ld_volatile_f64(src + 2);
+    }
+    // ---- every block: wait for the `world` tags in its own window, add the slots in rank order
+    double ra = 0.0, rb = 0.0, rc = 0.0;
+    int failed = 0;
+    if (lane < p.world) {
+      const double* src = p.inbox + slot + size_t(lane) * 4;
+      const unsigned long long t0 = gtime_ns();
+      while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != tag) {
+        if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
+        if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
       }
-      failed = __any_sync(0xffffffffu, failed);
-      // rank-ordered sequential sum (world <= 32), identical on every rank
-      a = 0.0;
-      b = 0.0;
-      c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
-      for (int r = 0; r < p.world; ++r) {
-        a += __shfl_sync(0xffffffffu, ra, r);
-        b += __shfl_sync(0xffffffffu, rb, r);
-        const double t = __shfl_sync(0xffffffffu, rc, r);
-        c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
-      }
+      ra = ld_volatile_f64(src + 0);
+      rb = ld_volatile_f64(src + 1);
+      rc = ld_volatile_f64(src + 2);
+    }
+    failed = __any_sync(0xffffffffu, failed);
+    double a = 0.0, b = 0.0;
+    double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
+    for (int r = 0; r < p.world; ++r) {      // rank-ordered sequential sum (world <= 32), same bits everywhere
+      a += __shfl_sync(0xffffffffu, ra, r);
+      b += __shfl_sync(0xffffffffu, rb, r);
+      const double t = __shfl_sync(0xffffffffu, rc, r);
+      c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
     }
     if (lane == 0) {
       sh.total[0] = a;
@@ -722,7 +718,10 @@ int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStr
   if (rc != RLVI_OK) return rc;
   p.control = reinterpret_cast<unsigned int*>(scratch);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + ctrl);
-  RLVI_CUDA(cudaMemsetAsync(p.control, 0, 64, stream));
+  // [0,64): ticket counter + failure flag; [256,512): the local window used when world == 1 (4 slots x 4
+  // doubles, tags start at 1 so the zeroed window never matches)
+  RLVI_CUDA(cudaMemsetAsync(p.control, 0, 512, stream));
+  if (p.world == 1) p.inbox = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
   void* args[] = {&p};
   RLVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kFpThreads), args,
                                         0, stream));

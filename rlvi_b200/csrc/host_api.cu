@@ -59,11 +59,16 @@ extern "C" int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, c
   }
   int rc = rlvi_fixed_point_f64(ctx, RLVI_FP_STANDARD, nullptr, nullptr, dE, n, tol, maxiter, dPi, dRes, nullptr, ks);
   if (rc != RLVI_OK) return rc;
+  // pi goes back over PCIe on the copy stream while the statistics kernel runs on the compute stream
+  if (pi_host) {
+    RLVI_CUDA(cudaEventRecord(ctx->ev[0], ks));
+    RLVI_CUDA(cudaStreamWaitEvent(cs, ctx->ev[0], 0));
+    RLVI_CUDA(cudaMemcpyAsync(pi_host, dPi, size_t(n) * 8, cudaMemcpyDeviceToHost, cs));
+  }
   rc = rlvi_weighted_moments_f64(ctx, dX, nullptr, dPi, n, d, 1, 1, dMom, ks);
   if (rc != RLVI_OK) return rc;
   RLVI_CUDA(cudaMemcpyAsync(moments_host, dMom, size_t(nm) * 8, cudaMemcpyDeviceToHost, ks));
   RLVI_CUDA(cudaMemcpyAsync(result_host, dRes, sizeof(rlvi_fp_result), cudaMemcpyDeviceToHost, ks));
-  if (pi_host) RLVI_CUDA(cudaMemcpyAsync(pi_host, dPi, size_t(n) * 8, cudaMemcpyDeviceToHost, ks));
   RLVI_CUDA(cudaStreamSynchronize(ks));
   RLVI_CUDA(cudaStreamSynchronize(cs));
   return RLVI_OK;

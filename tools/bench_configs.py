@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configs that are parity cases rather than bench lines
+(configs[2..4]) and for the drop-in outer loops.  One JSON object per line on stdout.
+
+  config 3  robust PCA M-step + losses, FP64, N = 2^20, d = 512 (generic Gram kernel; 4 GiB of X)
+  config 4  online E-step on HAR-shaped batches (100 x 60), per-batch launch latency
+  config 5  deep path: fused weighted CE fwd+bwd (8192 x 100), per-epoch E-step + threshold (N = 45 000),
+            each next to the reference's own torch ops (oracle/deep_ref.py restates them) ON THE SAME GPU
+  loops     rlvi.linear_regression / mean / logistic_regression(mm) end to end on device tensors
+
+Timing: CUDA events, 3 warm-ups, median of 10.  The oracle is used only as the baseline being compared to.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import deep_ref  # noqa: E402  (baseline only)
+from rlvi_b200 import deep, online, ops, rlvi, synth, utils  # noqa: E402
+
+dev = torch.device("cuda", 0)
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def config3():
+    n, d = 1 << 20, 512
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.randn((n, d), generator=g, device=dev, dtype=torch.float64)
+    w = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    theta = torch.randn(d, generator=g, device=dev, dtype=torch.float64)
+    theta /= theta.norm()
+    t_mom = timeit(lambda: ops.weighted_moments(X, w, power=2), reps=5)
+    t_loss = timeit(lambda: ops.loss(ops.LOSS_PCA, X, theta), reps=5)
+    t_blas = timeit(lambda: (X * (w * w)[:, None]).T @ X, reps=5)
+    emit(config="3: PCA statistics, FP64, N=2^20, d=512", gram_ms=t_mom, gram_tflops=n * d * (d + 1) / t_mom / 1e9,
+         loss_ms=t_loss, loss_GBps=n * (d + 1) * 8 / t_loss / 1e6, torch_cublas_gram_ms=t_blas)
+
+
+def config4():
+    rng = np.random.default_rng(1)
+    losses = torch.from_numpy(rng.exponential(0.7, size=100)).to(dev)
+    t = timeit(lambda: ops.fixed_point(losses, variant=ops.FP_ONLINE), reps=50)
+    lh = losses.cpu().numpy()
+    from oracle import rlvi_np
+    t0 = time.perf_counter()
+    for _ in range(200):
+        rlvi_np.update_weights_online(lh)
+    t_cpu = (time.perf_counter() - t0) / 200 * 1e3
+    emit(config="4: online E-step, batch of 100 (online-learning/main.py:45-58)", kernel_ms=t, numpy_cpu_ms=t_cpu,
+         note="single launch, latency-bound; the classifier update (sklearn SGD) is out of scope")
+
+
+def config5():
+    b, c, n_train = 8192, 100, 45000
+    logits_np, labels_np = synth.deep_batch(b, c, seed=1)
+    logits = torch.from_numpy(logits_np).to(dev)
+    labels = torch.from_numpy(labels_np).to(dev)
+    idx = torch.randperm(n_train, device=dev)[:b]
+    weights = torch.rand(n_train, device=dev)
+    residuals = torch.zeros(n_train, device=dev)
+
+    def fused():
+        ops.wce_fwd_bwd(logits, labels, weights, residuals, indexes=idx, want_correct=True)
+
+    def stock():                                   # train_rlvi.py:85,89-96 with stock torch ops
+        lg = logits.detach().requires_grad_(True)
+        out = torch.softmax(lg, dim=1)
+        _, pred = out.topk(5, 1, True, True)
+        pred.t().eq(labels.view(1, -1).expand_as(pred.t()))
+        loss = torch.nn.functional.cross_entropy(lg, labels, reduction="none")
+        residuals[idx] = loss.detach()
+        (loss * weights[idx]).mean().backward()
+
+    t_f, t_s = timeit(fused, reps=30), timeit(stock, reps=30)
+    emit(config="5a: weighted CE fwd+bwd + accuracy, 8192 x 100 FP32", fused_kernel_ms=t_f, stock_torch_ms=t_s,
+         speedup=t_s / t_f)
+
+    res0 = torch.from_numpy(np.random.default_rng(2).exponential(1.0, size=n_train).astype(np.float32)).to(dev)
+
+    def ours():
+        r, w = res0.clone(), torch.ones(n_train, device=dev)
+        deep.update_sample_weights(r, w)
+        ops.fn_threshold(w, truncate=True)
+
+    def ref():
+        r, w = res0.clone(), torch.ones(n_train, device=dev)
+        deep_ref.epoch_tail(r, w, True, 0)
+
+    t_o, t_r = timeit(ours, reps=20), timeit(ref, reps=20)
+    emit(config="5b: per-epoch E-step + threshold + truncation, N_train=45000 FP32", kernels_ms=t_o,
+         reference_torch_ops_same_gpu_ms=t_r, speedup=t_r / t_o)
+
+
+def loops():
+    n, d = 1 << 22, 64
+    X, y, theta = synth.logistic_shard_torch(n, d, dev, seed=5)
+    yl = (X @ torch.ones(d, dtype=torch.float64, device=dev)) + torch.randn(n, device=dev, dtype=torch.float64)
+    for name, fn in (("rlvi.mean", lambda: rlvi.mean(X)),
+                     ("rlvi.linear_regression", lambda: rlvi.linear_regression(X, yl)),
+                     ("rlvi.logistic_regression(mm)", lambda: rlvi.logistic_regression(X, y, mstep="mm")),
+                     ("utils.mm_log_reg", lambda: utils.mm_log_reg(X, y, torch.ones(n, dtype=torch.float64, device=dev)))):
+        torch.cuda.synchronize()
+        l0 = ops.launch_count(0)
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        emit(loop=name, n=n, d=d, wall_ms=(time.perf_counter() - t0) * 1e3, library_launches=ops.launch_count(0) - l0)
+
+
+if __name__ == "__main__":
+    config5()
+    config4()
+    config3()
+    loops()
