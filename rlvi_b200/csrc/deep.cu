@@ -4,7 +4,7 @@
 //                          (and utils.py:65-79 `accuracy`, called at train_rlvi.py:85) in ONE launch
 //                          instead of ~12 ATen kernels.
 //   rlvi_fn_threshold_f32  train_rlvi.py:41-49 (false_negative_criterion) + :102-103 (truncation)
-//                          as one single-CTA radix select instead of sort + cumsum + compare + index.
+//                          as one single-CTA bisection select instead of sort + cumsum + compare + index.
 #include <math.h>
 
 #include "common.cuh"
@@ -122,159 +122,137 @@ __global__ void __launch_bounds__(kWceThreads) wce_kernel(const WceParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// false-negative threshold: radix select over the FP32 bit patterns, masses in 2^-40 fixed point
+// false-negative threshold (train_rlvi.py:41-49): selection by bisection over the FP32 bit patterns.
+//
+// With the weights sorted descending, c_j = sum_{i<=j} (1 - w_(i)) and J = #{j : c_j <= beta}; the threshold
+// is w_(J) (J = 0 wraps to the smallest weight, quirk Q9).  M(tau) = sum_{w >= tau} (1 - w) is non-increasing
+// in tau, so tau* = min{tau : M(tau) <= beta} is found with <= 33 passes over the weights (cached in shared
+// memory), each one contention-free block reduction of a 64-bit fixed-point mass (2^-40 units: exact, order
+// independent).  Then P = #{w >= tau*}, and of the next lower weight value kappa (mass u each)
+// t = floor((beta - M(tau*)) / u) more elements fit:  J = P + t.
+// (A first version histogrammed 8-bit digits with shared-memory atomics: the weights of clean samples pile
+// into one or two bins and the atomics serialised, ~1 ms for 45 000 weights.)
 // ---------------------------------------------------------------------------------------------
 constexpr int kThrThreads = 1024;
 constexpr double kFix = 1099511627776.0;   // 2^40
-
-struct ThrShared {
-  unsigned int cnt[256];
-  unsigned long long mass[256];
-  unsigned long long red_mass[kThrThreads / 32];
-  unsigned int red_key[kThrThreads / 32];
-  // scalars broadcast by thread 0
-  unsigned int prefix;
-  unsigned long long P, M;
-  int done;
-  unsigned int result_key;
-  int need_pred;     // answer is the smallest key > prefix
-  int need_min;      // answer is the smallest weight
-};
 
 __device__ __forceinline__ unsigned long long mass_of(float w) {
   const float u = 1.0f - w;                      // the FP32 value torch forms (line 46)
   return u > 0.f ? (unsigned long long)__double2ll_rn(double(u) * kFix) : 0ull;
 }
 
-__global__ void __launch_bounds__(kThrThreads) fn_threshold_kernel(float* weights, int64_t n, float alpha,
-                                                                   float prev_threshold, int truncate,
-                                                                   float* out_threshold) {
-  __shared__ ThrShared sh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- pass 0: total mass and the smallest key
+struct ThrRed {
+  unsigned long long m[2][kThrThreads / 32];
+  unsigned int c[2][kThrThreads / 32];
+};
+
+// block-wide sums of a 64-bit mass and a 32-bit count; every thread gets both totals; one __syncthreads
+__device__ __forceinline__ void thr_allreduce(ThrRed& red, unsigned long long& m, unsigned int& c, unsigned int& round) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int b = round & 1u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m += __shfl_xor_sync(0xffffffffu, m, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) {
+    red.m[b][warp] = m;
+    red.c[b][warp] = c;
+  }
+  __syncthreads();
+  m = red.m[b][lane];
+  c = red.c[b][lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m += __shfl_xor_sync(0xffffffffu, m, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  round += 1u;
+}
+__device__ __forceinline__ unsigned int thr_allmin(ThrRed& red, unsigned int v, unsigned int& round, bool want_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int b = round & 1u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = want_max ? max(v, t) : min(v, t);
+  }
+  if (lane == 0) red.c[b][warp] = v;
+  __syncthreads();
+  v = red.c[b][lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = want_max ? max(v, t) : min(v, t);
+  }
+  round += 1u;
+  return v;
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(kThrThreads, 1) fn_threshold_kernel(float* weights, int64_t n, float alpha,
+                                                                      float prev_threshold, int truncate,
+                                                                      float* out_threshold) {
+  extern __shared__ __align__(16) unsigned char thr_smem[];
+  __shared__ ThrRed red;
+  unsigned int* skeys = reinterpret_cast<unsigned int*>(thr_smem);
+  const unsigned int* keys = CACHED ? skeys : reinterpret_cast<const unsigned int*>(weights);
+  const int tid = threadIdx.x;
+  unsigned int round = 0;
+  // ---- pass 0: cache the keys, total mass, smallest key
   unsigned long long tm = 0ull;
-  unsigned int kmin = 0xffffffffu;
+  unsigned int kmin = 0xffffffffu, cnt0 = 0u;
   for (int64_t i = tid; i < n; i += kThrThreads) {
     const float w = weights[i];
+    if (CACHED) skeys[i] = __float_as_uint(w);
     tm += mass_of(w);
     kmin = min(kmin, __float_as_uint(w));
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    tm += __shfl_xor_sync(0xffffffffu, tm, o);
-    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-  }
-  if (lane == 0) {
-    sh.red_mass[warp] = tm;
-    sh.red_key[warp] = kmin;
-  }
-  __syncthreads();
-  unsigned long long beta_fix = 0ull;
-  unsigned int key_min = 0xffffffffu;
-  {
-    unsigned long long t = 0ull;
-    for (int w = 0; w < kThrThreads / 32; ++w) {
-      t += sh.red_mass[w];
-      key_min = min(key_min, sh.red_key[w]);
-    }
-    const float total = float(double(t) / kFix);          // torch.sum(1 - weights): FP32 scalar
-    const float beta = total * alpha;                     // line 44
-    beta_fix = (unsigned long long)(double(beta) * kFix);
-  }
-  if (tid == 0) {
-    sh.prefix = 0u;
-    sh.P = 0ull;
-    sh.M = 0ull;
-    sh.done = 0;
-    sh.need_pred = 0;
-    sh.need_min = 0;
-    sh.result_key = 0u;
-  }
-  __syncthreads();
+  thr_allreduce(red, tm, cnt0, round);                    // also orders the key cache (its __syncthreads)
+  const unsigned int key_min = thr_allmin(red, kmin, round, false);
+  const float total = float(double(tm) / kFix);           // torch.sum(1 - weights): FP32 scalar
+  const float beta = total * alpha;                       // line 44
+  const unsigned long long beta_fix = (unsigned long long)(double(beta) * kFix);
 
-  // ---- four 8-bit levels, most significant first (weights >= 0: bit pattern order == value order)
-  for (int level = 0; level < 4 && !sh.done; ++level) {
-    const int shift = 24 - 8 * level;
-    const unsigned int himask = level == 0 ? 0u : (0xffffffffu << (shift + 8));
-    if (tid < 256) {
-      sh.cnt[tid] = 0u;
-      sh.mass[tid] = 0ull;
+  unsigned int result_key;
+  if (tm <= beta_fix) {
+    result_key = key_min;                                 // everything fits: index n-1 -> the smallest weight
+  } else {
+    // ---- largest tau_f with M(tau_f) > beta, bit by bit; tau* = tau_f + 1   (M(0) = total > beta here)
+    unsigned int cur = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned int cand = cur | (1u << bit);
+      unsigned long long m = 0ull;
+      unsigned int c = 0u;
+      for (int64_t i = tid; i < n; i += kThrThreads) {
+        const unsigned int k = keys[i];
+        if (k >= cand) m += mass_of(__uint_as_float(k));
+      }
+      thr_allreduce(red, m, c, round);
+      if (m > beta_fix) cur = cand;
     }
-    __syncthreads();
-    const unsigned int prefix = sh.prefix;
+    // cur = tau_f is an actual key (the largest key whose "keys >= it" mass exceeds beta) = kappa
+    const unsigned int kappa = cur;
+    unsigned long long m_hi = 0ull;
+    unsigned int p_hi = 0u, c_kappa = 0u, key_hi = 0xffffffffu;
     for (int64_t i = tid; i < n; i += kThrThreads) {
-      const float w = weights[i];
-      const unsigned int key = __float_as_uint(w);
-      if ((key & himask) == prefix) {
-        const unsigned int b = (key >> shift) & 255u;
-        atomicAdd(&sh.cnt[b], 1u);
-        atomicAdd(&sh.mass[b], mass_of(w));
+      const unsigned int k = keys[i];
+      if (k > kappa) {
+        m_hi += mass_of(__uint_as_float(k));
+        ++p_hi;
+        key_hi = min(key_hi, k);
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long P = sh.P, M = sh.M;
-      int b = 255;
-      for (; b >= 0; --b) {
-        if (M + sh.mass[b] > beta_fix) break;   // this bucket does not fit entirely
-        P += sh.cnt[b];
-        M += sh.mass[b];
-      }
-      sh.P = P;
-      sh.M = M;
-      if (b < 0) {
-        // everything under this prefix fits: the boundary is at the end of the prefix range
-        if (level == 0) {
-          sh.need_min = 1;           // all n weights fit: index n-1 -> the smallest weight
-        } else {
-          // cannot happen: the parent level chose this bucket because it did NOT fit entirely
-          sh.need_min = 1;
-        }
-        sh.done = 1;
-      } else {
-        sh.prefix = prefix | (unsigned int)(b) << shift;
-        if (level == 3) {
-          const unsigned int key = sh.prefix;
-          const unsigned long long u = mass_of(__uint_as_float(key));
-          const unsigned long long room = beta_fix - M;          // M <= beta_fix here
-          unsigned long long t = (u == 0ull) ? sh.cnt[b] : room / u;
-          if (t > sh.cnt[b]) t = sh.cnt[b];
-          if (t >= 1ull) {
-            sh.result_key = key;
-          } else if (P == 0ull) {
-            sh.need_min = 1;          // nothing fits: index -1 wraps to the smallest weight (Q9)
-          } else {
-            sh.need_pred = 1;         // boundary falls just before this key: previous (larger) key
-          }
-          sh.done = 1;
-        }
-      }
-    }
-    __syncthreads();
+    thr_allreduce(red, m_hi, p_hi, round);
+    key_hi = thr_allmin(red, key_hi, round, false);
+    const unsigned long long u = mass_of(__uint_as_float(kappa));     // > 0: else M(kappa) = M(kappa+1) <= beta
+    const unsigned long long t = (beta_fix - m_hi) / (u ? u : 1ull);  // elements of value kappa that still fit
+    (void)c_kappa;
+    if (t >= 1ull) result_key = kappa;
+    else if (p_hi >= 1u) result_key = key_hi;
+    else result_key = key_min;                            // nothing fits: index -1 wraps (quirk Q9)
   }
-
-  if (sh.need_pred) {
-    const unsigned int key = sh.prefix;
-    unsigned int best = 0xffffffffu;
-    for (int64_t i = tid; i < n; i += kThrThreads) {
-      const unsigned int k = __float_as_uint(weights[i]);
-      if (k > key) best = min(best, k);
-    }
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    __syncthreads();
-    if (lane == 0) sh.red_key[warp] = best;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int b = 0xffffffffu;
-      for (int w = 0; w < kThrThreads / 32; ++w) b = min(b, sh.red_key[w]);
-      sh.result_key = b;
-    }
-    __syncthreads();
-  } else if (sh.need_min) {
-    if (tid == 0) sh.result_key = key_min;
-    __syncthreads();
-  }
-  const float thr_new = __uint_as_float(sh.result_key);
-  const float thr = fmaxf(prev_threshold, thr_new);          // line 102
+  const float thr = fmaxf(prev_threshold, __uint_as_float(result_key));   // line 102
   if (tid == 0) out_threshold[0] = thr;
   if (truncate) {
     for (int64_t i = tid; i < n; i += kThrThreads) {
@@ -363,8 +341,17 @@ extern "C" int rlvi_fn_threshold_f32(rlvi_ctx* ctx, float* weights, int64_t n, f
   RLVI_REQUIRE(n > 0, "n must be positive");
   RLVI_REQUIRE(n < (int64_t(1) << 22), "single-CTA selection supports n < 2^22");
   RlviDeviceGuard guard(ctx->device);
-  fn_threshold_kernel<<<1, kThrThreads, 0, static_cast<cudaStream_t>(stream)>>>(weights, n, alpha, prev_threshold,
-                                                                              truncate, out_threshold);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t cache = (size_t(n) * 4 + 15) & ~size_t(15);
+  if (cache <= size_t(200) * 1024) {
+    RLVI_CUDA(cudaFuncSetAttribute(fn_threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+    fn_threshold_kernel<true><<<1, kThrThreads, cache, st>>>(weights, n, alpha, prev_threshold, truncate,
+                                                             out_threshold);
+  } else {
+    fn_threshold_kernel<false><<<1, kThrThreads, 0, st>>>(weights, n, alpha, prev_threshold, truncate,
+                                                          out_threshold);
+  }
   RLVI_LAUNCH_CHECK(ctx);
   return RLVI_OK;
 }

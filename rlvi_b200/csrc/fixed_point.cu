@@ -67,6 +67,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   double v;
   asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -149,8 +157,12 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
         dst[0] = a;
         dst[1] = b;
         dst[2] = c;
-        __threadfence_system();
-        st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
+        if (p.world > 1) {      // peers read it over NVLink: system scope
+          __threadfence_system();
+          st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
+        } else {                // single GPU: device scope is enough (and cheaper)
+          st_release_gpu_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
+        }
       }
     }
     // ---- every block: wait for the `world` tags in its own window, add the slots in rank order
@@ -159,7 +171,8 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     if (lane < p.world) {
       const double* src = p.inbox + slot + size_t(lane) * 4;
       const unsigned long long t0 = gtime_ns();
-      while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(src + 3)) != tag) {
+      const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 3);
+      while ((p.world > 1 ? ld_acquire_sys_u64(flag) : ld_acquire_gpu_u64(flag)) != tag) {
         if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
         if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
       }
@@ -359,15 +372,27 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, doub
     s2a += t2a;
     s2b += t2b;
   }
-  for (; c < nvec; c += stride) {
-    const double2 v = ld_e2(ev + c);
-    double pn, d;
-    post_pair_f64<VARIANT>(v.x, rho_new, rho_old, pn, d);
-    s1a += pn;
-    s2a = fma(d, d, s2a);
-    post_pair_f64<VARIANT>(v.y, rho_new, rho_old, pn, d);
-    s1b += pn;
-    s2b = fma(d, d, s2b);
+  if (c < nvec) {
+    // remainder: ONE predicated trip with all loads in flight together (a chunk-at-a-time tail loop costs a
+    // full memory latency per chunk, which dominated the pass once a shard is L2 resident)
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      const int64_t i = c + u * stride;
+      v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      if (c + u * stride < nvec) {
+        double pn, d;
+        post_pair_f64<VARIANT>(v[u].x, rho_new, rho_old, pn, d);
+        s1a += pn;
+        s2a = fma(d, d, s2a);
+        post_pair_f64<VARIANT>(v[u].y, rho_new, rho_old, pn, d);
+        s1b += pn;
+        s2b = fma(d, d, s2b);
+      }
+    }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     double pn, d;
@@ -406,10 +431,20 @@ __device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, doubl
       one(v[u].y, s1b, s2b);
     }
   }
-  for (; c < nvec; c += stride) {
-    const double2 v = ld_e2(ev + c);
-    one(v.x, s1a, s2a);
-    one(v.y, s1b, s2b);
+  if (c < nvec) {
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      const int64_t i = c + u * stride;
+      v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      if (c + u * stride < nvec) {
+        one(v[u].x, s1a, s2a);
+        one(v[u].y, s1b, s2b);
+      }
+    }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) one(e[n - 1], s1a, s2a);
   s1 = s1a + s1b;
@@ -437,9 +472,18 @@ __device__ __forceinline__ void final_pass_vec(const double* e, double* out, int
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) ov[c + u * stride] = make_double2(one(v[u].x), one(v[u].y));
   }
-  for (; c < nvec; c += stride) {
-    const double2 v = ld_e2(ev + c);
-    ov[c] = make_double2(one(v.x), one(v.y));
+  if (c < nvec) {
+    double2 v[kFpUnroll];
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      const int64_t i = c + u * stride;
+      v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u) {
+      const int64_t i = c + u * stride;
+      if (i < nvec) ov[i] = make_double2(one(v[u].x), one(v[u].y));
+    }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = one(e[n - 1]);
 }
@@ -699,6 +743,183 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_deep_f32(const FpParams<
   }
 }
 
+// =================================================================================================
+// Small-n path: the WHOLE loop in one CTA, e[] resident in shared memory (n <= 28 K doubles / 56 K floats:
+// the online batches of 100 and the deep path's N_train = 45 000).  No grid barrier, no global traffic
+// between passes: a pass is n/1024 shared-memory reads per thread plus one block reduction (~1-2 us).
+// =================================================================================================
+constexpr int kSmallThreads = 1024;
+constexpr size_t kSmallSmemBytes = size_t(224) * 1024;
+
+struct SmallRed {
+  double part[2][3][kSmallThreads / 32];
+};
+
+// Block-wide reduction of three values (v2 with OP2); every thread returns the totals.  Fixed order: xor tree
+// per warp, then every warp adds the 32 warp partials in the same lane-strided order.  One __syncthreads per
+// call (the partial buffers alternate by `round` parity).
+template <int OP2>
+__device__ __forceinline__ void block_allreduce3(SmallRed& red, double& v0, double& v1, double& v2, unsigned int& round) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int b = round & 1u;
+  v0 = warp_sum(v0);
+  v1 = warp_sum(v1);
+  v2 = (OP2 == OP_SUM) ? warp_sum(v2) : (OP2 == OP_MIN ? warp_min(v2) : warp_max(v2));
+  if (lane == 0) {
+    red.part[b][0][warp] = v0;
+    red.part[b][1][warp] = v1;
+    red.part[b][2][warp] = v2;
+  }
+  __syncthreads();
+  v0 = warp_sum(red.part[b][0][lane]);
+  v1 = warp_sum(red.part[b][1][lane]);
+  const double t = red.part[b][2][lane];
+  v2 = (OP2 == OP_SUM) ? warp_sum(t) : (OP2 == OP_MIN ? warp_min(t) : warp_max(t));
+  round += 1u;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kSmallThreads, 1) fp_small_kernel_f64(const FpParams<double> p) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  double* se = reinterpret_cast<double*>(small_smem);
+  __shared__ SmallRed red;
+  unsigned int round = 0;
+  const int n = int(p.n);
+  const double n_glob = double(p.n_global);
+  const double pi0 = (VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5;
+  const double s = p.scale ? *p.scale : 1.0;
+  double eps = 1.0 - pi0;
+  double rho_new = (VARIANT == RLVI_FP_STANDARD) ? eps / (1.0 - eps) : pi0 / (1.0 - pi0);
+  double rho_old = 0.0;
+  // pass 1: e -> shared memory (+ global e_work, part of the contract), sums against the constant pi0
+  double s1 = 0.0, s2 = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += kSmallThreads) {
+    const double ev = p.losses ? exp(-(s * p.losses[i])) : p.e[i];
+    se[i] = ev;
+    if (p.losses) p.e[i] = ev;
+    const double pn = post_f64<VARIANT>(ev, rho_new);
+    const double d = pn - pi0;
+    s1 += pn;
+    s2 = fma(d, d, s2);
+    mx = fmax(mx, ev);
+  }
+  block_allreduce3<OP_MAX>(red, s1, s2, mx, round);
+  const double emax = mx;
+  double S = s1, err = sqrt(s2);
+  int k = 1, converged = 0;
+  while (true) {
+    if (err < p.tol) { converged = 1; break; }
+    if (k >= p.maxiter) break;
+    rho_old = rho_new;
+    const double avg = S / n_glob;
+    eps = 1.0 - avg;
+    rho_new = (VARIANT == RLVI_FP_STANDARD) ? eps / (1.0 - eps) : avg / (1.0 - avg);
+    ++k;
+    double a1 = 0.0, a2 = 0.0, z = 0.0;
+    for (int i = threadIdx.x; i < n; i += kSmallThreads) {
+      double pn, d;
+      post_pair_f64<VARIANT>(se[i], rho_new, rho_old, pn, d);
+      a1 += pn;
+      a2 = fma(d, d, a2);
+    }
+    block_allreduce3<OP_SUM>(red, a1, a2, z, round);
+    S = a1;
+    err = sqrt(a2);
+  }
+  double norm = 1.0;
+  if (VARIANT == RLVI_FP_ONLINE) norm = post_f64<VARIANT>(emax, rho_new) * n_glob;
+  for (int i = threadIdx.x; i < n; i += kSmallThreads) {
+    double pv = post_f64<VARIANT>(se[i], rho_new);
+    if (VARIANT == RLVI_FP_ONLINE) pv = pv / norm;
+    p.pi_out[i] = pv;
+  }
+  if (threadIdx.x == 0) {
+    rlvi_fp_result r;
+    r.eps = eps;
+    r.rho = rho_new;
+    r.sum_pi = S;
+    r.err = err;
+    r.iters = k;
+    r.converged = converged;
+    *p.result = r;
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) fp_small_kernel_deep_f32(const FpParams<float> p) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  float* se = reinterpret_cast<float*>(small_smem);
+  __shared__ SmallRed red;
+  unsigned int round = 0;
+  const int n = int(p.n);
+  const double n_glob = double(p.n_global);
+  float* res = p.residuals;
+  float* wts = p.pi_out;
+  double mn = INFINITY, z0 = 0.0, z1 = 0.0;
+  for (int i = threadIdx.x; i < n; i += kSmallThreads) mn = fmin(mn, double(res[i]));
+  block_allreduce3<OP_MIN>(red, z0, z1, mn, round);
+  const float rmin = float(mn);
+  float rho_new = float(0.95 / (1.0 - 0.95)), rho_old = 0.0f, avg = 0.95f;
+  double s1 = 0.0, s2 = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += kSmallThreads) {
+    const float r = res[i] - rmin;           // residuals.sub_(min)
+    const float ev = expf(-r);               // torch.exp(-residuals)
+    res[i] = r;
+    se[i] = ev;
+    p.e[i] = ev;
+    const float pn = post_f32(ev, rho_new);
+    const float d = pn - wts[i];             // first pass: against the INCOMING weights
+    s1 += double(pn);
+    s2 = fma(double(d), double(d), s2);
+    mx = fmax(mx, double(ev));
+  }
+  block_allreduce3<OP_MAX>(red, s1, s2, mx, round);
+  const double emax = mx;
+  double S = s1, err = double(float(sqrt(s2)));
+  int k = 1, converged = 0;
+  while (true) {
+    avg = float(S / n_glob);                 // weights.mean(), computed BEFORE the test (train_rlvi.py:34-35)
+    rho_old = rho_new;
+    const float rho_next = __fdiv_rn(avg, 1.0f - avg);
+    if (float(err) < float(p.tol)) { converged = 1; break; }
+    if (k >= p.maxiter) break;
+    rho_new = rho_next;
+    ++k;
+    double a1 = 0.0, a2 = 0.0, z = 0.0;
+    for (int i = threadIdx.x; i < n; i += kSmallThreads) {
+      const float ev = se[i];
+      const float pn = post_f32(ev, rho_new);
+      const float d = pn - post_f32(ev, rho_old);
+      a1 += double(pn);
+      a2 = fma(double(d), double(d), a2);
+    }
+    block_allreduce3<OP_SUM>(red, a1, a2, z, round);
+    S = a1;
+    err = double(float(sqrt(a2)));
+  }
+  const float rho_fin = rho_old;
+  const float wmax = post_f32(float(emax), rho_fin);
+  for (int i = threadIdx.x; i < n; i += kSmallThreads) wts[i] = __fdiv_rn(post_f32(se[i], rho_fin), wmax);
+  if (threadIdx.x == 0) {
+    rlvi_fp_result r;
+    r.eps = 1.0 - double(avg);
+    r.rho = double(rho_fin);
+    r.sum_pi = S;
+    r.err = err;
+    r.iters = k;
+    r.converged = converged;
+    *p.result = r;
+  }
+}
+
+template <typename T, typename K>
+int launch_fp_small(rlvi_ctx* ctx, K kernel, const FpParams<T>& p, cudaStream_t stream) {
+  const size_t smem = (size_t(p.n) * sizeof(T) + 15) & ~size_t(15);
+  RLVI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmallSmemBytes)));
+  kernel<<<1, kSmallThreads, smem, stream>>>(p);
+  RLVI_LAUNCH_CHECK(ctx);
+  return RLVI_OK;
+}
+
 // ---- host launch -----------------------------------------------------------------------------
 template <typename T, typename K>
 int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStream_t stream) {
@@ -780,6 +1001,9 @@ extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* lo
   const bool vec = rlvi_aligned16(e_work) && rlvi_aligned16(pi_out) && (!losses || rlvi_aligned16(losses));
   const int64_t chunks = vec ? (n + 1) / 2 : n;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.world == 1 && size_t(n) * sizeof(double) <= kSmallSmemBytes && losses != pi_out)
+    return variant == RLVI_FP_STANDARD ? launch_fp_small(ctx, fp_small_kernel_f64<RLVI_FP_STANDARD>, p, st)
+                                       : launch_fp_small(ctx, fp_small_kernel_f64<RLVI_FP_ONLINE>, p, st);
   if (variant == RLVI_FP_STANDARD)
     return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, true>, p, chunks, st)
                : launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, false>, p, chunks, st);
@@ -808,6 +1032,8 @@ extern "C" int rlvi_fixed_point_deep_f32(rlvi_ctx* ctx, float* residuals, float*
   const bool vec = rlvi_aligned16(residuals) && rlvi_aligned16(weights) && rlvi_aligned16(e_work);
   const int64_t chunks = vec ? (n + 3) / 4 : n;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.world == 1 && size_t(n) * sizeof(float) <= kSmallSmemBytes)
+    return launch_fp_small(ctx, fp_small_kernel_deep_f32, p, st);
   return vec ? launch_fp(ctx, fp_kernel_deep_f32<true>, p, chunks, st)
              : launch_fp(ctx, fp_kernel_deep_f32<false>, p, chunks, st);
 }
