@@ -600,7 +600,13 @@ extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const d
     return RLVI_OK;
   }
 
-  // ---- generic path: vectors first, then the Gram ------------------------------------------------
+  // ---- general d on the FP64 tensor pipe, TMA tensor-map fed (gram_tma.cu) --------------------------
+  if (want_gram) {
+    const int trc = rlvi_gram_tma_f64(ctx, X, y, weights, n, d, power, want_gram, out, st);
+    if (trc != RLVI_ERR_UNSUPPORTED) return trc;
+  }
+
+  // ---- fallback (odd d, unaligned pointers, tiny n): vectors first, then a register-tiled Gram ------
   int rc = run_colsum<0>(ctx, X, y, weights, nullptr, n, d, power, out, 2 + 2 * d, st);
   if (rc != RLVI_OK) return rc;
   if (!want_gram) return RLVI_OK;

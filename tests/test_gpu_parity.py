@@ -257,7 +257,8 @@ def test_gaussian_loss_against_oracle(dev, n, d):
 # weighted M-step statistics
 # ==================================================================================================
 MOM_SHAPES = [(1, 1), (7, 2), (40, 10), (257, 31), (1000, 33), (63, 64), (64, 64), (65, 64), (4096 + 17, 64),
-              (100000, 64), (777, 65), (500, 100), (300, 512), (150, 1000)]
+              (100000, 64), (777, 65), (500, 100), (300, 512), (150, 1000), (64, 16), (20001, 128), (5000, 256),
+              (4096 + 17, 512), (2000, 1024), (3000, 130)]
 
 
 @pytest.mark.parametrize("n,d", MOM_SHAPES)
