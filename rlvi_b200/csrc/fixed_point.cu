@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kFpThreads = 256;
 constexpr int kFpUnroll = 8;            // independent 128-bit loads in flight per thread
+constexpr int kFpCacheSlots = 26;       // 26 x 256 x 16 B = 104 KiB of e[] per CTA stay in shared memory (2 CTAs/SM)
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 enum ReduceOp { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
@@ -47,6 +48,7 @@ struct FpParams {
   double* inbox;
   double* const* peer_inbox;
   unsigned long long call_index;
+  int cache_slots;        // FP64 VEC kernels: chunks per thread kept in shared memory
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -305,6 +307,18 @@ __device__ __forceinline__ double2 ld_e2(const double2* p) {
   asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
   return r;
 }
+// On-chip residency of e[] between passes: the first `slots` chunks of every thread (chunk ordinal =
+// 8 trip + u) are kept in shared memory (filled during pass 1), the rest is re-read from L2 / HBM.  At 8 GPUs a
+// shard is 64 MiB and ~40 % of it fits the 148 x ~216 KB of shared memory, which cuts the L2 traffic of the
+// L2-bound passes by that much; the values are identical to the global ones, so results do not change.
+struct ECache {
+  double2* buf;    // [slots][blockDim.x]
+  int slots;
+};
+__device__ __forceinline__ double2 ld_e2c(const ECache& ec, int slot, const double2* gptr) {
+  return (slot < ec.slots) ? ec.buf[slot * kFpThreads + threadIdx.x] : ld_e2(gptr);
+}
+
 // Branch-free fast evaluation of (pi', pi' - pi); `ok` is cleared when the operand left the safe range,
 // in which case the caller redoes the whole trip with post_pair_f64's IEEE divisions.
 template <int VARIANT>
@@ -329,18 +343,19 @@ __device__ __forceinline__ void post_pair_fast(double e, double rho_new, double 
 }
 
 template <int VARIANT>
-__device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, double rho_new, double rho_old,
-                                                double& s1, double& s2) {
+__device__ __forceinline__ void stream_pass_vec(const double* e, const ECache& ec, int64_t n, double rho_new,
+                                                double rho_old, double& s1, double& s2) {
   const double2* ev = reinterpret_cast<const double2*>(e);
   const int64_t nvec = n >> 1;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   const double drho = rho_old - rho_new;
   int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
-  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+  int slot0 = 0;
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
     double2 v[kFpUnroll];
 #pragma unroll
-    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2c(ec, slot0 + u, ev + c + u * stride);
     double t1a = 0.0, t1b = 0.0, t2a = 0.0, t2b = 0.0;
     bool ok = true;
 #pragma unroll
@@ -357,7 +372,7 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, doub
       t1a = t1b = t2a = t2b = 0.0;
 #pragma unroll 1
       for (int u = 0; u < kFpUnroll; ++u) {
-        const double2 w = ld_e2(ev + c + u * stride);   // re-load: keeps v[] in registers on the fast path
+        const double2 w = ld_e2c(ec, slot0 + u, ev + c + u * stride);   // re-load: keeps v[] in registers
         double pn, d;
         post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
         t1a += pn;
@@ -379,7 +394,7 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, doub
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
       const int64_t i = c + u * stride;
-      v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+      v[u] = (i < nvec) ? ld_e2c(ec, slot0 + u, ev + i) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
@@ -407,8 +422,8 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, int64_t n, doub
 // Pass 1 over a precomputed, 16-byte aligned e[] (the loss kernel wrote it): pi' against the constant
 // initial posterior, plus max e (ONLINE's normalisation).  Same load batching as stream_pass_vec.
 template <int VARIANT>
-__device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, double rho, double pi0, double& s1,
-                                               double& s2, double& mx) {
+__device__ __forceinline__ void first_pass_vec(const double* e, const ECache& ec, int64_t n, double rho, double pi0,
+                                               double& s1, double& s2, double& mx) {
   const double2* ev = reinterpret_cast<const double2*>(e);
   const int64_t nvec = n >> 1;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -421,10 +436,14 @@ __device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, doubl
     sb = fma(d, d, sb);
     m = fmax(m, x);
   };
-  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+  int slot0 = 0;
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
     double2 v[kFpUnroll];
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+#pragma unroll
+    for (int u = 0; u < kFpUnroll; ++u)
+      if (slot0 + u < ec.slots) ec.buf[(slot0 + u) * kFpThreads + threadIdx.x] = v[u];
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
       one(v[u].x, s1a, s2a);
@@ -437,6 +456,7 @@ __device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, doubl
     for (int u = 0; u < kFpUnroll; ++u) {
       const int64_t i = c + u * stride;
       v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+      if (i < nvec && slot0 + u < ec.slots) ec.buf[(slot0 + u) * kFpThreads + threadIdx.x] = v[u];
     }
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
@@ -454,7 +474,8 @@ __device__ __forceinline__ void first_pass_vec(const double* e, int64_t n, doubl
 
 // Final pass: pi = the reference's own expression (IEEE division), optionally divided by `norm` (ONLINE).
 template <int VARIANT>
-__device__ __forceinline__ void final_pass_vec(const double* e, double* out, int64_t n, double rho, double norm) {
+__device__ __forceinline__ void final_pass_vec(const double* e, const ECache& ec, double* out, int64_t n, double rho,
+                                               double norm) {
   const double2* ev = reinterpret_cast<const double2*>(e);
   double2* ov = reinterpret_cast<double2*>(out);
   const int64_t nvec = n >> 1;
@@ -465,10 +486,11 @@ __device__ __forceinline__ void final_pass_vec(const double* e, double* out, int
     if (VARIANT == RLVI_FP_ONLINE) pv = pv / norm;
     return pv;
   };
-  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride) {
+  int slot0 = 0;
+  for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
     double2 v[kFpUnroll];
 #pragma unroll
-    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
+    for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2c(ec, slot0 + u, ev + c + u * stride);
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) ov[c + u * stride] = make_double2(one(v[u].x), one(v[u].y));
   }
@@ -477,7 +499,7 @@ __device__ __forceinline__ void final_pass_vec(const double* e, double* out, int
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
       const int64_t i = c + u * stride;
-      v[u] = (i < nvec) ? ld_e2(ev + i) : make_double2(0.0, 0.0);
+      v[u] = (i < nvec) ? ld_e2c(ec, slot0 + u, ev + i) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
@@ -502,6 +524,12 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   const double* losses = p.losses;
   double* e = p.e;
   constexpr int W = VEC ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char fp_dyn_smem[];
+  ECache ec;
+  ec.buf = reinterpret_cast<double2*>(fp_dyn_smem);
+  ec.slots = VEC ? p.cache_slots : 0;
+  const int64_t chunk0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t cstride = int64_t(gridDim.x) * blockDim.x;
 
   // rho for pass 1 from the constant initial posterior, in the reference's operation order
   double rho_new, rho_old = 0.0, eps;
@@ -519,7 +547,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   for (;; ++k) {
     double s1 = 0.0, s2 = 0.0, mx = 0.0;
     if (k == 1 && VEC && !have_losses) {
-      first_pass_vec<VARIANT>(e, p.n, rho_new, pi0, s1, s2, mx);
+      first_pass_vec<VARIANT>(e, ec, p.n, rho_new, pi0, s1, s2, mx);
     } else if (k == 1) {
       for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
         const int64_t i = c * W;
@@ -533,6 +561,10 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
         } else {
           load_chunk<double, VEC, W>(e, i, p.n, ev, 0.0);
         }
+        if (VEC) {   // keep the chunk on chip for the later passes (chunk ordinal of this thread = slot)
+          const int64_t slot = (c - chunk0) / cstride;
+          if (slot < ec.slots && i + W <= p.n) ec.buf[slot * kFpThreads + threadIdx.x] = make_double2(ev[0], ev[W - 1]);
+        }
 #pragma unroll
         for (int j = 0; j < W; ++j) {
           if (i + j < p.n) {
@@ -545,7 +577,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
         }
       });
     } else if (VEC) {
-      stream_pass_vec<VARIANT>(e, p.n, rho_new, rho_old, s1, s2);
+      stream_pass_vec<VARIANT>(e, ec, p.n, rho_new, rho_old, s1, s2);
     } else {
       for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
         const int64_t i = c * W;
@@ -592,7 +624,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   double norm = 1.0;
   if (VARIANT == RLVI_FP_ONLINE) norm = post_f64<VARIANT>(emax, rho_new) * n_glob;   // max(pi') * n
   if (ok && VEC) {
-    final_pass_vec<VARIANT>(e, p.pi_out, p.n, rho_new, norm);
+    final_pass_vec<VARIANT>(e, ec, p.pi_out, p.n, rho_new, norm);
   } else if (ok) {
     double* out = p.pi_out;
     for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
@@ -922,9 +954,13 @@ int launch_fp_small(rlvi_ctx* ctx, K kernel, const FpParams<T>& p, cudaStream_t 
 
 // ---- host launch -----------------------------------------------------------------------------
 template <typename T, typename K>
-int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStream_t stream) {
+int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStream_t stream, int cache_slots = 0) {
   int per_sm = 0;
-  RLVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFpThreads, 0));
+  const size_t dyn_smem = size_t(cache_slots) * kFpThreads * sizeof(double2);
+  p.cache_slots = cache_slots;
+  if (dyn_smem > 0)
+    RLVI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
+  RLVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFpThreads, dyn_smem));
   if (per_sm < 1) {
     rlvi_set_error("fixed-point kernel does not fit on an SM");
     return RLVI_ERR_CUDA;
@@ -945,7 +981,7 @@ int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStr
   if (p.world == 1) p.inbox = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
   void* args[] = {&p};
   RLVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kFpThreads), args,
-                                        0, stream));
+                                        dyn_smem, stream));
   RLVI_LAUNCH_CHECK(ctx);
   return RLVI_OK;
 }
@@ -1005,9 +1041,9 @@ extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* lo
     return variant == RLVI_FP_STANDARD ? launch_fp_small(ctx, fp_small_kernel_f64<RLVI_FP_STANDARD>, p, st)
                                        : launch_fp_small(ctx, fp_small_kernel_f64<RLVI_FP_ONLINE>, p, st);
   if (variant == RLVI_FP_STANDARD)
-    return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, true>, p, chunks, st)
+    return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, true>, p, chunks, st, kFpCacheSlots)
                : launch_fp(ctx, fp_kernel_f64<RLVI_FP_STANDARD, false>, p, chunks, st);
-  return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_ONLINE, true>, p, chunks, st)
+  return vec ? launch_fp(ctx, fp_kernel_f64<RLVI_FP_ONLINE, true>, p, chunks, st, kFpCacheSlots)
              : launch_fp(ctx, fp_kernel_f64<RLVI_FP_ONLINE, false>, p, chunks, st);
 }
 

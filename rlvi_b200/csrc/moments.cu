@@ -250,11 +250,19 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
 // Sum the per-CTA partials in CTA order and scatter to the public layout.
 __global__ void gram64_finalize_kernel(const double* __restrict__ partials, int nparts, int want_gram,
                                        double* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= kPartialStride) return;
-  if (!want_gram && e >= 2 + 2 * kD) return;
+  // four lanes per output element: lane q adds the CTA partials c = q, q + 4, ... in order, then a fixed
+  // two-level shuffle tree (148 dependent loads per thread made this 15 us; it matters once a GPU's shard of
+  // the statistics pass takes ~1 ms)
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid >> 2, q = gid & 3;
   double s = 0.0;
-  for (int c = 0; c < nparts; ++c) s += partials[size_t(c) * kPartialStride + e];
+  if (e < kPartialStride && (want_gram || e < 2 + 2 * kD)) {
+    for (int c = q; c < nparts; c += 4) s += partials[size_t(c) * kPartialStride + e];
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (q != 0 || e >= kPartialStride) return;
+  if (!want_gram && e >= 2 + 2 * kD) return;
   if (e < 2 + 2 * kD) {
     out[e] = s;
     return;
@@ -595,7 +603,7 @@ extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const d
       gram64_kernel<false><<<grid, kGramThreads, kGramSmem, st>>>(p);
     }
     RLVI_LAUNCH_CHECK(ctx);
-    gram64_finalize_kernel<<<(kPartialStride + 255) / 256, 256, 0, st>>>(p.partials, grid, want_gram, out);
+    gram64_finalize_kernel<<<(4 * kPartialStride + 255) / 256, 256, 0, st>>>(p.partials, grid, want_gram, out);
     RLVI_LAUNCH_CHECK(ctx);
     return RLVI_OK;
   }
