@@ -252,6 +252,12 @@ def run_b200(args):
                 "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
                 "step_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak,   # per GPU
                 "kernels": kernels}
+    # the statistics pass is bounded by the FP64 tensor pipe, not by HBM: report that too
+    gram_flops = n * 36 * 512 / 4          # 36 DMMA.8x8x4 (512 flop) per 4 rows
+    roofline["fp64_tensor"] = {"kernel": "gram64_kernel", "achieved": gram_flops / (kms[2] * 1e-3) / 1e12, "peak": 36.9,
+                               "unit": "TFLOP/s", "frac": gram_flops / (kms[2] * 1e-3) / 1e12 / 36.9,
+                               "peak_source": "measured DMMA.8x8x4 issue rate, tools/ubench_dmma.cu "
+                                              "(profiles/r01_ubench_dmma.txt); not in MEASURED_PEAKS.json"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:

@@ -99,6 +99,16 @@ int rlvi_dist_window_open(rlvi_ctx* ctx, int rank, int world, void* own_window,
                           const unsigned char* all_handles, void** peer_table_out);
 int rlvi_dist_window_close(rlvi_ctx* ctx, int rank, int world, void* own_window, void* peer_table);
 
+/* All-reduce (SUM) of a small FP64 statistics vector over the ranks WITHOUT NCCL: every rank stores its
+ * `count` doubles into slot `rank` of every peer's window over NVLink, publishes a sequence tag, waits for the
+ * `world` tags in its own window and adds the slots in rank order -- every rank ends with the same bits in
+ * `buf` (in place).  One launch; replaces the NCCL all-reduce of the d*d + 2d + 2 statistics after
+ * rlvi_weighted_moments_f64.  count <= RLVI_DIST_STATS_CAPACITY; `dist->call_index`
+ * must be 1, 2, 3, ... identically on every rank (its own sequence, independent of the fixed-point calls).
+ * The window is the one created by rlvi_dist_window_create (it reserves the statistics area). */
+#define RLVI_DIST_STATS_CAPACITY 8192
+int rlvi_stats_allreduce_f64(rlvi_ctx* ctx, double* buf, int count, const rlvi_fp_dist* dist, void* stream);
+
 /* FP64 fixed point (STANDARD or ONLINE).
  *   losses   [n]  per-sample loss l_i, or NULL when `e_work` already holds e_i = exp(-l_i)
  *   scale    device scalar s or NULL (=1): the kernel uses e_i = exp(-s * l_i); lets the caller fold

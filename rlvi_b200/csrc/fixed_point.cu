@@ -1011,7 +1011,11 @@ int fill_dist(FpParams<T>& p, const rlvi_fp_dist* dist, int64_t n) {
 
 }  // namespace
 
-extern "C" int rlvi_fp_dist_inbox_doubles(int world) { return 4 * world * 4; }
+// window layout (doubles): [0, 16 world) fixed-point slots | [16 world, 18 world) statistics tags (2 parities) |
+// then 2 parities x world x RLVI_DIST_STATS_CAPACITY statistics slots (dist.cu)
+extern "C" int rlvi_fp_dist_inbox_doubles(int world) {
+  return 16 * world + 2 * world + 2 * world * RLVI_DIST_STATS_CAPACITY;
+}
 
 extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
                                     double* e_work, int64_t n, double tol, int maxiter, double* pi_out,

@@ -529,10 +529,240 @@ int launch_colsum(rlvi_ctx* ctx, const RowMapCfg& cfg, ColParams& p, int grid, s
   return RLVI_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed column sums (d % 16 == 0, d <= 256, 16-byte aligned pointers): same skeleton as loss_tma_kernel
+// (loss.cu) -- one producer lane per consumer warp, private rings, ONE bulk copy per 32-row tile.
+//   phase 1 (MODE 1 only): lane = row, rotated conflict-free walk, phi = b + x.theta,
+//                          c1 = w (sigmoid(phi) - y)                       utils.py:40-41
+//           (MODE 0)      : c1 = w, c2 = we * y                           rlvi.py:48,56,71,80
+//   phase 2: lane = feature pair(s): acc[f] += c_r * x[r][f] over the 32 rows of the tile, c_r broadcast from
+//            shared memory; every 128-bit read of x is one conflict-free wavefront per 8 lanes.
+// Per-warp d-vectors are summed in warp order, per-CTA partials in CTA order (sum_parts_kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kCtConsumers = 16;
+constexpr int kCtThreads = (kCtConsumers + 1) * 32;
+constexpr int kCtRows = 32;
+constexpr int kCtMaxStages = 2 * kCtConsumers;
+
+struct ColTmaParams {
+  const double* X;
+  const double* y;
+  const double* w;
+  const double* params;
+  int64_t n;
+  int d;
+  int power;
+  int stage_bytes;   // kCtRows * d * 8 + 512 (y, w)
+  int ncons, depth;
+  double* partials;  // [grid][2 + 2 d]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = p.ncons, R = p.depth, S = C * R;
+  unsigned char* ring = smem_raw;
+  double* sTheta = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);          // d (+ 2)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sTheta + p.d + 2);
+  uint64_t* empty_bar = full_bar + kCtMaxStages;
+  double* sC = reinterpret_cast<double*>(empty_bar + kCtMaxStages);                      // [C][2][32] row coefficients
+  double* sOut = sC + kCtConsumers * 64;                                                  // [C][2 + 2 d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = p.d, npair = d >> 1;
+  const int stride = 2 + 2 * d;
+  if (MODE == 1)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) sTheta[i] = p.params[1 + i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double b0 = (MODE == 1) ? p.params[0] : 0.0;
+  const int64_t ntiles = (p.n + kCtRows - 1) / kCtRows;
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t tile_bytes = uint32_t(kCtRows) * uint32_t(d) * 8u;
+  const bool has_y = p.y != nullptr;
+
+  if (warp == kCtConsumers) {
+    if (lane < C) {
+      int64_t r = 0;
+      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
+        const int stage = lane * R + int(r % R);
+        const uint32_t phase = uint32_t(r / R) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+        double* sY = reinterpret_cast<double*>(sX + tile_bytes);
+        double* sW = sY + kCtRows;
+        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kCtRows;
+        if (row0 + kCtRows <= p.n) {
+          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + 256u + (has_y ? 256u : 0u));
+          bulk_g2s(sX, p.X + row0 * d, tile_bytes, &full_bar[stage]);
+          if (has_y) bulk_g2s(sY, p.y + row0, 256, &full_bar[stage]);
+          bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
+        } else {
+          const int rows = int(p.n - row0);
+          for (int i = 0; i < kCtRows; ++i) {       // rows past n: w = 0 -> no contribution (x there is stale but finite)
+            sY[i] = (has_y && i < rows) ? p.y[row0 + i] : 0.0;
+            sW[i] = (i < rows) ? p.w[row0 + i] : 0.0;
+          }
+          // stale rows could hold NaN bit patterns from an earlier tile of another call: clear them
+          double* sXd = reinterpret_cast<double*>(sX);
+          for (int i = rows * d; i < kCtRows * d; ++i) sXd[i] = 0.0;
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(d) * 8u);
+          bulk_g2s(sX, p.X + row0 * d, uint32_t(rows) * uint32_t(d) * 8u, &full_bar[stage]);
+        }
+      }
+    }
+  } else if (warp < C) {
+    const double2* th2 = reinterpret_cast<const double2*>(sTheta);
+    double* myC = sC + warp * 64;
+    constexpr int kMaxUnitsPerLane = 4;          // d <= 256 -> <= 128 units of 16 bytes per row
+    double a1[2 * kMaxUnitsPerLane], a2[2 * kMaxUnitsPerLane];
+#pragma unroll
+    for (int i = 0; i < 2 * kMaxUnitsPerLane; ++i) {
+      a1[i] = 0.0;
+      a2[i] = 0.0;
+    }
+    double s0 = 0.0, swy = 0.0;
+    for (int64_t t = warp; t < my_tiles; t += C) {
+      const int64_t r = t / C;
+      const int stage = warp * R + int(r % R);
+      const uint32_t phase = uint32_t(r / R) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+      const double* sY = reinterpret_cast<const double*>(sX + tile_bytes);
+      const double* sW = sY + kCtRows;
+      const double2* xt = reinterpret_cast<const double2*>(sX);
+      // ---- phase 1: one row per lane -> its coefficients
+      const double w1 = sW[lane];
+      const double yi = has_y ? sY[lane] : 0.0;
+      double c1, c2 = 0.0;
+      if (MODE == 0) {
+        const double we = (p.power == 2) ? w1 * w1 : w1;
+        c1 = w1;
+        c2 = we * yi;
+        s0 += we;
+        swy += c2;
+      } else {
+        const double2* xr = xt + size_t(lane) * npair;
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+        int u = lane % npair;
+#pragma unroll 4
+        for (int j = 0; j < npair; j += 2) {
+          int u1 = u + 1;
+          if (u1 == npair) u1 = 0;
+          const double2 x0 = xr[u], x1 = xr[u1];
+          const double2 t0 = th2[u], t1 = th2[u1];
+          u = u1 + 1;
+          if (u == npair) u = 0;
+          q0 = fma(x0.x, t0.x, q0);
+          q1 = fma(x0.y, t0.y, q1);
+          q2 = fma(x1.x, t1.x, q2);
+          q3 = fma(x1.y, t1.y, q3);
+        }
+        const double phi = b0 + ((q0 + q1) + (q2 + q3));
+        const double z = exp(-fabs(phi));                       // utils.py:7-16 sigmoid, overflow-free form
+        const double sg = (phi >= 0.0 ? 1.0 : z) / (1.0 + z);
+        c1 = w1 * (sg - yi);
+        s0 += c1;
+      }
+      myC[lane] = c1;
+      if (MODE == 0) myC[32 + lane] = c2;
+      __syncwarp();
+      // ---- phase 2: lane = feature pair(s); acc += c_r * x[r][.] over the tile's rows
+#pragma unroll 4
+      for (int rr = 0; rr < kCtRows; ++rr) {
+        const double k1 = myC[rr];
+        const double k2 = (MODE == 0) ? myC[32 + rr] : 0.0;
+        const double2* xrow = xt + size_t(rr) * npair;
+#pragma unroll
+        for (int v = 0; v < kMaxUnitsPerLane; ++v) {
+          const int unit = lane + 32 * v;
+          if (unit < npair) {
+            const double2 x = xrow[unit];
+            a1[2 * v] = fma(k1, x.x, a1[2 * v]);
+            a1[2 * v + 1] = fma(k1, x.y, a1[2 * v + 1]);
+            if (MODE == 0) {
+              a2[2 * v] = fma(k2, x.x, a2[2 * v]);
+              a2[2 * v + 1] = fma(k2, x.y, a2[2 * v + 1]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+    // per-warp vector to shared memory
+    double* mine = sOut + size_t(warp) * stride;
+    s0 = warp_sum(s0);
+    swy = warp_sum(swy);
+    if (lane == 0) {
+      mine[0] = s0;
+      mine[1] = swy;
+    }
+#pragma unroll
+    for (int v = 0; v < kMaxUnitsPerLane; ++v) {
+      const int unit = lane + 32 * v;
+      if (unit < npair) {
+        mine[2 + 2 * unit] = a1[2 * v];
+        mine[2 + 2 * unit + 1] = a1[2 * v + 1];
+        mine[2 + d + 2 * unit] = a2[2 * v];
+        mine[2 + d + 2 * unit + 1] = a2[2 * v + 1];
+      }
+    }
+  }
+  __syncthreads();
+  double* out = p.partials + size_t(blockIdx.x) * stride;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < C; ++w) s += sOut[size_t(w) * stride + e];
+    out[e] = s;
+  }
+}
+
 // shared host driver for the two colsum modes; result lands in out[0 .. 2+2d)
 template <int MODE>
 int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w, const double* params, int64_t n,
                int d, int power, double* out, int count, cudaStream_t st) {
+  // ---- TMA-fed path -------------------------------------------------------------------------------
+  if (d % 16 == 0 && d <= 256 && n >= kCtRows && rlvi_aligned16(X) && rlvi_aligned16(w) && (!y || rlvi_aligned16(y))) {
+    ColTmaParams q;
+    q.X = X;
+    q.y = y;
+    q.w = w;
+    q.params = params;
+    q.n = n;
+    q.d = d;
+    q.power = power;
+    q.stage_bytes = kCtRows * d * 8 + 512;
+    const int stride = 2 + 2 * d;
+    const size_t tail = size_t(d + 2) * 8 + 2 * kCtMaxStages * 8 + size_t(kCtConsumers) * 64 * 8 +
+                        size_t(kCtConsumers) * stride * 8 + 128;
+    const int max_stages = int((size_t(224) * 1024 - tail) / q.stage_bytes);
+    q.ncons = max_stages < kCtConsumers ? max_stages : kCtConsumers;
+    q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
+    if (q.depth > 2) q.depth = 2;
+    if (q.ncons >= 2) {
+      const int64_t ntiles = (n + kCtRows - 1) / kCtRows;
+      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
+      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+      void* scratch = nullptr;
+      int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * stride * sizeof(double), &scratch);
+      if (rc != RLVI_OK) return rc;
+      q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
+      const size_t smem = size_t(q.ncons) * q.depth * q.stage_bytes + tail;
+      RLVI_CUDA(cudaFuncSetAttribute(colsum_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      colsum_tma_kernel<MODE><<<grid, kCtThreads, smem, st>>>(q);
+      RLVI_LAUNCH_CHECK(ctx);
+      sum_parts_kernel<<<(count + 255) / 256, 256, 0, st>>>(q.partials, grid, stride, count, MODE == 1 ? 1 : 0, out);
+      RLVI_LAUNCH_CHECK(ctx);
+      return RLVI_OK;
+    }
+  }
+
   RowMapCfg cfg;
   if (!rowmap_pick(d, rlvi_aligned16(X), &cfg)) {
     rlvi_set_error("column-sum kernels support 1 <= d <= 1024 (got %d)", d);

@@ -6,8 +6,10 @@ Only sums couple the shards:
   * the fixed point's three partial sums per pass are exchanged INSIDE the persistent kernel through
     NVLink peer windows (rlvi_dist_window_* + rlvi_fp_dist) and summed in rank order, so every rank gets
     the same bits and takes the same stop decision;
-  * the d x d / d-vector statistics of the M-step are all-reduced once per step with NCCL
-    (`ShardGroup.all_reduce`; gloo on CPU tensors in the unit tests).
+  * the d x d / d-vector statistics of the M-step are all-reduced once per step
+    (`ShardGroup.all_reduce`): up to 8192 doubles through the library's own peer-window kernel
+    (rlvi_stats_allreduce_f64 -- remote stores over NVLink, rank-ordered sum), larger ones with NCCL;
+    gloo on CPU tensors in the unit tests.
 The reference has no distributed code at all; this module is new.
 """
 from __future__ import annotations
@@ -43,6 +45,7 @@ class ShardGroup:
         self.window = None
         self.table = None
         self.calls = 0
+        self.stats_calls = 0
         self._ctx = None
 
     @classmethod
@@ -87,11 +90,24 @@ class ShardGroup:
         return _lib.FpDist(self.rank, self.world, int(n_global), self.window, self.table, self.calls)
 
     # ---- statistics ----------------------------------------------------------------------------
+    STATS_CAPACITY = 8192     # RLVI_DIST_STATS_CAPACITY
+
     def all_reduce(self, t: torch.Tensor):
-        """In-place SUM over the ranks (NCCL over NVLink on CUDA; NVLS in-switch reduction when NCCL
-        picks it).  Every rank receives the same bits."""
-        if self.world > 1:
-            td.all_reduce(t, op=td.ReduceOp.SUM)
+        """In-place SUM over the ranks; every rank receives the same bits.  FP64 CUDA vectors of up to
+        STATS_CAPACITY elements (the d*d + 2d + 2 statistics for d <= 88) go through the library's own
+        peer-window kernel (rlvi_stats_allreduce_f64: remote stores over NVLink + rank-ordered sum, one
+        launch); anything else through torch.distributed (NCCL on CUDA, gloo on CPU)."""
+        if self.world == 1:
+            return t
+        if (self.window is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and t.numel() <= self.STATS_CAPACITY):
+            self.stats_calls += 1
+            d = _lib.FpDist(self.rank, self.world, 0, self.window, self.table, self.stats_calls)
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self._ctx.lib.rlvi_stats_allreduce_f64(self._ctx.handle, C.c_void_p(t.data_ptr()), t.numel(),
+                                                              C.byref(d), stream), "rlvi_stats_allreduce_f64")
+            return t
+        td.all_reduce(t, op=td.ReduceOp.SUM)
         return t
 
     def close(self):

@@ -299,6 +299,28 @@ def test_weighted_moments_no_gram_and_determinism(dev):
     assert not c[2 + 2 * d:].any()
 
 
+@pytest.mark.parametrize("n,d", [(300001, 64), (50001, 32), (9999, 256)])
+def test_moments_without_gram_tma_path(dev, n, d):
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d)) + 0.2
+    y = rng.normal(size=n)
+    w = rng.random(n)
+    for power in (1, 2):
+        for use_y in (True, False):
+            out = ops.weighted_moments(cu(X, dev), cu(w, dev), y=cu(y, dev) if use_y else None, power=power,
+                                       want_gram=False)
+            m = {k: v.cpu().numpy() for k, v in ops.split_moments(out, d).items()}
+            we = w ** power
+            assert abs(m["S0"] - we.sum()) < 1e-12 * we.sum()
+            assert relmax(m["S1"], X.T @ w) < 1e-12
+            if use_y:
+                assert relmax(m["Sy"], X.T @ (we * y)) < 1e-12
+                assert abs(m["Swy"] - we @ y) < 1e-12 * np.abs(we * y).sum()
+            else:
+                assert not m["Sy"].any() and m["Swy"] == 0.0
+
+
 def test_weighted_moments_linearity_large(dev):
     """Size-independent property at a size the oracle cannot reach quickly: moments are linear in w."""
     from rlvi_b200 import ops
@@ -315,7 +337,8 @@ def test_weighted_moments_linearity_large(dev):
     assert float((ops.split_moments(m12, d)["G"] - G).abs().max() / G.abs().max()) < 1e-12
 
 
-@pytest.mark.parametrize("n,d", [(40, 10), (1031, 64), (777, 65), (300, 512)])
+@pytest.mark.parametrize("n,d", [(40, 10), (1031, 64), (777, 65), (300, 512), (300001, 64), (70001, 128), (9999, 256),
+                                 (33, 16)])
 def test_logistic_grad_against_oracle(dev, n, d):
     from rlvi_b200 import ops
     rng = np.random.default_rng(n + d)
