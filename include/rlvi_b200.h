@@ -120,6 +120,13 @@ int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const
                          double* e_work, int64_t n, double tol, int maxiter, double* pi_out,
                          rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
 
+/* Same, starting from the initial posterior `pi0` in (0, 1) instead of the variant's constant.  The reference
+ * restarts every online batch from 0.5 (online-learning/main.py:48, quirk Q11); carrying the previous batch's
+ * mean posterior (1 - result.eps) into the next call is the OPT-IN extension BASELINE.json's config 4 names. */
+int rlvi_fixed_point_init_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                              double* e_work, int64_t n, double tol, int maxiter, double pi0, double* pi_out,
+                              rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
+
 /* FP32 fixed point, DEEP variant: `residuals` [n] and `weights` [n] are both updated in place,
  * exactly as methods/train_rlvi.py:14-38 leaves them.  `e_work` [n] is FP32 scratch. */
 int rlvi_fixed_point_deep_f32(rlvi_ctx* ctx, float* residuals, float* weights, float* e_work, int64_t n,

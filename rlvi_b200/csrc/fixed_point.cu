@@ -49,6 +49,7 @@ struct FpParams {
   double* const* peer_inbox;
   unsigned long long call_index;
   int cache_slots;        // FP64 VEC kernels: chunks per thread kept in shared memory
+  double pi0;             // initial posterior; 0 = the variant's constant (0.95 / 0.5)
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   __shared__ FpShared sh;
   unsigned int round = 0;
   const double n_glob = double(p.n_global);
-  const double pi0 = (VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5;
+  const double pi0 = (p.pi0 > 0.0) ? p.pi0 : ((VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5);
   const double s = p.scale ? *p.scale : 1.0;
   const bool have_losses = p.losses != nullptr;
   const double* losses = p.losses;
@@ -818,7 +819,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) fp_small_kernel_f64(const Fp
   unsigned int round = 0;
   const int n = int(p.n);
   const double n_glob = double(p.n_global);
-  const double pi0 = (VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5;
+  const double pi0 = (p.pi0 > 0.0) ? p.pi0 : ((VARIANT == RLVI_FP_STANDARD) ? 0.95 : 0.5);
   const double s = p.scale ? *p.scale : 1.0;
   double eps = 1.0 - pi0;
   double rho_new = (VARIANT == RLVI_FP_STANDARD) ? eps / (1.0 - eps) : pi0 / (1.0 - pi0);
@@ -1017,9 +1018,27 @@ extern "C" int rlvi_fp_dist_inbox_doubles(int world) {
   return 16 * world + 2 * world + 2 * world * RLVI_DIST_STATS_CAPACITY;
 }
 
+static int fixed_point_f64_impl(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                                double* e_work, int64_t n, double tol, int maxiter, double pi0, double* pi_out,
+                                rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
+
 extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
                                     double* e_work, int64_t n, double tol, int maxiter, double* pi_out,
                                     rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream) {
+  return fixed_point_f64_impl(ctx, variant, losses, scale, e_work, n, tol, maxiter, 0.0, pi_out, result, dist, stream);
+}
+
+extern "C" int rlvi_fixed_point_init_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                                         double* e_work, int64_t n, double tol, int maxiter, double pi0,
+                                         double* pi_out, rlvi_fp_result* result, const rlvi_fp_dist* dist,
+                                         void* stream) {
+  RLVI_REQUIRE(pi0 > 0.0 && pi0 < 1.0, "pi0 must be in (0, 1)");
+  return fixed_point_f64_impl(ctx, variant, losses, scale, e_work, n, tol, maxiter, pi0, pi_out, result, dist, stream);
+}
+
+static int fixed_point_f64_impl(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
+                                double* e_work, int64_t n, double tol, int maxiter, double pi0, double* pi_out,
+                                rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream) {
   RLVI_REQUIRE(ctx && e_work && pi_out && result, "null pointer");
   RLVI_REQUIRE(n > 0, "n must be positive");
   RLVI_REQUIRE(maxiter >= 1, "maxiter must be >= 1");
@@ -1038,6 +1057,7 @@ extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* lo
   p.result = result;
   int rc = fill_dist(p, dist, n);
   if (rc != RLVI_OK) return rc;
+  p.pi0 = pi0;
   const bool vec = rlvi_aligned16(e_work) && rlvi_aligned16(pi_out) && (!losses || rlvi_aligned16(losses));
   const int64_t chunks = vec ? (n + 1) / 2 : n;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

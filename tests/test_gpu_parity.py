@@ -134,6 +134,59 @@ def test_online_fixed_point_golden(dev):
         assert relmax(online.update_weights_rlvi(l), rlvi_np.update_weights_online(l)) < F64_TOL
 
 
+def test_online_carry_over_extension(dev):
+    """Opt-in extension: start a batch from the previous batch's mean posterior instead of 0.5."""
+    from rlvi_b200 import online
+    rng = np.random.default_rng(8)
+    l1, l2 = rng.exponential(0.8, size=100), rng.exponential(0.8, size=100)
+
+    def ref(losses, w0):      # online-learning/main.py:45-58 with weights = w0 instead of 0.5
+        e = np.exp(-losses)
+        w = np.full_like(losses, w0)
+        for _ in range(100):
+            avg = np.mean(w)
+            rho = avg / (1 - avg)
+            new = rho * e / (1 + rho * e)
+            if np.linalg.norm(new - w) < 1e-3:
+                break
+            w = new.copy()
+        return new / (np.max(new) * len(new)), np.mean(new)
+
+    w1, avg1 = online.update_weights_rlvi(l1, return_avg=True)
+    r1, ravg1 = ref(l1, 0.5)
+    assert relmax(w1, r1) < F64_TOL and abs(avg1 - ravg1) < F64_TOL
+    w2 = online.update_weights_rlvi(l2, init_weight=avg1)
+    assert relmax(w2, ref(l2, ravg1)[0]) < F64_TOL
+    assert relmax(w2, rlvi_np.update_weights_online(l2)) > 1e-6      # really different from the 0.5 restart
+
+
+def test_c_abi_error_codes(dev):
+    """Bad arguments come back as negative codes + message (never a crash, never a silent fallback)."""
+    from rlvi_b200 import _lib, ops
+    x = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.RlviError, match="maxiter"):
+        ops.fixed_point(x, maxiter=0)
+    with pytest.raises(_lib.RlviError, match="alias"):
+        ops.fixed_point(x, e_work=x, out=x)
+    with pytest.raises(_lib.RlviError, match="pi0"):
+        ops.fixed_point(x, pi0=1.5)
+    X = torch.zeros((8, 2000), dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.RlviError, match="1 <= d <= 1024"):
+        ops.loss(ops.LOSS_PCA, X, torch.zeros(2000, dtype=torch.float64, device=dev))
+    with pytest.raises(_lib.RlviError, match="needs y"):
+        ops.loss(ops.LOSS_SQRES, X[:, :8].contiguous(), torch.zeros(8, dtype=torch.float64, device=dev))
+    with pytest.raises(_lib.RlviError, match="power"):
+        ops.weighted_moments(X[:, :8].contiguous(), torch.ones(8, dtype=torch.float64, device=dev), power=3)
+    with pytest.raises(_lib.RlviError, match="classes"):
+        ops.wce_fwd_bwd(torch.zeros((2, 2048), device=dev), torch.zeros(2, dtype=torch.int64, device=dev),
+                        torch.ones(2, device=dev), torch.zeros(2, device=dev))
+    with pytest.raises(TypeError):
+        ops.fixed_point(torch.zeros(4, dtype=torch.float64))               # CPU tensor: no CPU path
+    # the library is still healthy afterwards
+    pi, _ = ops.fixed_point(torch.rand(100, dtype=torch.float64, device=dev))
+    assert torch.isfinite(pi).all()
+
+
 @pytest.mark.parametrize("tag", ["n50", "n3000"])
 def test_update_weights_constrained_golden(dev, tag):
     from rlvi_b200 import rlvi
