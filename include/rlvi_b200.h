@@ -184,6 +184,14 @@ int rlvi_moments_out_doubles(int d);
 int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
                               int64_t n, int d, int power, int want_gram, double* out, void* stream);
 
+/* Same statistics about a centre c[d] (device array): every x_i is replaced by (x_i - c), i.e.
+ * G = sum w (x-c)(x-c)^T, S1 = sum weights (x-c), Sy = sum w y (x-c); S0, Swy unchanged.  utils.py:103-105
+ * centres the samples at the weighted mean before forming the covariance; one pass for the mean
+ * (want_gram = 0) followed by one centred pass reproduces that without the cancellation of G/S0 - mu mu^T. */
+int rlvi_weighted_moments_centered_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
+                                       const double* center, int64_t n, int d, int power, int want_gram,
+                                       double* out, void* stream);
+
 /* utils.py:40-41  the MM/gradient step's data term:  out[0] = sum c_i, out[1..d] = X^T c with
  * c_i = w_i (sigmoid(b + x_i.theta) - y_i);  params = [b, theta(d)].  `out` = device double[d+1]. */
 int rlvi_logistic_grad_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,

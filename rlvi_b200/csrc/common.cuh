@@ -32,8 +32,8 @@ struct rlvi_ctx {
 void rlvi_set_error(const char* fmt, ...);
 int rlvi_scratch(rlvi_ctx* ctx, size_t bytes, void** out);   // grows ctx->scratch if needed
 // gram_tma.cu: general-d Gram on the FP64 tensor pipe; RLVI_ERR_UNSUPPORTED = shape not covered (fall back)
-int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights, int64_t n, int d,
-                      int power, int want_gram, double* out, cudaStream_t st);
+int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights, const double* center,
+                      int64_t n, int d, int power, int want_gram, double* out, cudaStream_t st);
 
 #define RLVI_CUDA(expr)                                                                   \
   do {                                                                                    \

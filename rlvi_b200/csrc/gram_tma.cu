@@ -66,6 +66,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
 struct GramTmaParams {
   const double* y;
   const double* w;
+  const double* center;   // optional: x_i - center
   int64_t n;
   int d;
   int power;
@@ -88,9 +89,9 @@ __device__ __forceinline__ void load_frag(const unsigned char* tile, int r, int 
 
 // ---- diagonal unit (bi == bj): 36 upper-triangular tiles per warp, every warp takes 2 of the 16 k-groups of
 // a tile; S0, Swy, S1, Sy ride along -----------------------------------------------------------------
-template <bool HAS_Y>
+template <bool HAS_Y, bool CENTERED>
 __device__ __forceinline__ void consume_diag(const GramTmaParams& p, unsigned char* ring, uint64_t* full_bar,
-                                             uint64_t* empty_bar, int64_t ntiles, double* smG, double* out) {
+                                             uint64_t* empty_bar, int64_t ntiles, double* smG, double* out, int bi) {
   constexpr int NT = 36;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -98,12 +99,15 @@ __device__ __forceinline__ void consume_diag(const GramTmaParams& p, unsigned ch
   double acc[2 * NT];
   double s1[8], sy[8];
   double s0 = 0.0, swy = 0.0;
+  double ca[8];
 #pragma unroll
   for (int i = 0; i < 2 * NT; ++i) acc[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     s1[i] = 0.0;
     sy[i] = 0.0;
+    const int f = bi * kB + feat_of64(i, g);
+    ca[i] = (CENTERED && f < p.d) ? p.center[f] : 0.0;
   }
   int stage = 0;
   uint32_t phase = 0;
@@ -117,6 +121,10 @@ __device__ __forceinline__ void consume_diag(const GramTmaParams& p, unsigned ch
       const int r = (warp + kGConsumers * kk) * 4 + t;
       double xa[8];
       load_frag(sA, r, cidx, xa);
+      if (CENTERED) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xa[j] -= ca[j];
+      }
       const double w1 = sW[r];
       const double we = (p.power == 2) ? w1 * w1 : w1;
       double wy = 0.0;
@@ -198,8 +206,10 @@ __device__ __forceinline__ void consume_diag(const GramTmaParams& p, unsigned ch
 
 // ---- off-diagonal unit (bi < bj): all 64 tiles.  Warps 0-3 own the tile rows I = 0..3, warps 4-7 the rows
 // I = 4..7 (32 tiles = 64 accumulator registers per lane); each warp takes 4 of the 16 k-groups of a tile. ----
+template <bool CENTERED>
 __device__ __forceinline__ void consume_offdiag(const GramTmaParams& p, unsigned char* ring, uint64_t* full_bar,
-                                                uint64_t* empty_bar, int64_t ntiles, double* smG, double* out) {
+                                                uint64_t* empty_bar, int64_t ntiles, double* smG, double* out, int bi,
+                                                int bj) {
   constexpr int NT = 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -208,6 +218,17 @@ __device__ __forceinline__ void consume_offdiag(const GramTmaParams& p, unsigned
   double acc[2 * NT];
 #pragma unroll
   for (int i = 0; i < 2 * NT; ++i) acc[i] = 0.0;
+  double cbv[8], cav[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int f = bj * kB + feat_of64(j, g);
+    cbv[j] = (CENTERED && f < p.d) ? p.center[f] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = bi * kB + feat_of64(4 * ih + i, g);
+    cav[i] = (CENTERED && f < p.d) ? p.center[f] : 0.0;
+  }
   int stage = 0;
   uint32_t phase = 0;
   for (int64_t tile = 0; tile < ntiles; ++tile) {
@@ -226,7 +247,11 @@ __device__ __forceinline__ void consume_offdiag(const GramTmaParams& p, unsigned
       const double2 v1 = *reinterpret_cast<const double2*>(abase + kBoxBytes);
       const double w1 = sW[r];
       const double we = (p.power == 2) ? w1 * w1 : w1;
-      const double a[4] = {we * v0.x, we * v0.y, we * v1.x, we * v1.y};
+      if (CENTERED) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xb[j] -= cbv[j];
+      }
+      const double a[4] = {we * (v0.x - cav[0]), we * (v0.y - cav[1]), we * (v1.x - cav[2]), we * (v1.y - cav[3])};
 #pragma unroll
       for (int I = 0; I < 4; ++I) {
 #pragma unroll
@@ -255,7 +280,7 @@ __device__ __forceinline__ void consume_offdiag(const GramTmaParams& p, unsigned
   }
 }
 
-template <bool HAS_Y>
+template <bool HAS_Y, bool CENTERED>
 __global__ void __launch_bounds__(kGThreads, 1) gram_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                 const GramTmaParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -334,9 +359,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_tma_kernel(const __grid_con
     double* out = p.partials + size_t(unit) * kUnitStride;
     double* smG = reinterpret_cast<double*>(ring);
     if (diag)
-      consume_diag<HAS_Y>(p, ring, full_bar, empty_bar, ntiles, smG, out);
+      consume_diag<HAS_Y, CENTERED>(p, ring, full_bar, empty_bar, ntiles, smG, out, bi);
     else
-      consume_offdiag(p, ring, full_bar, empty_bar, ntiles, smG, out);
+      consume_offdiag<CENTERED>(p, ring, full_bar, empty_bar, ntiles, smG, out, bi, bj);
   }
 }
 
@@ -394,8 +419,8 @@ __global__ void gram_tma_finalize_kernel(const double* __restrict__ partials, in
 }  // namespace
 
 // Returns RLVI_OK, or RLVI_ERR_UNSUPPORTED when this path does not apply (caller falls back).
-int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights, int64_t n, int d,
-                      int power, int want_gram, double* out, cudaStream_t st) {
+int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights, const double* center,
+                      int64_t n, int d, int power, int want_gram, double* out, cudaStream_t st) {
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode || d % 2 != 0 || d < 16 || d > 2048 || n < kRows || n >= (int64_t(1) << 31) || !rlvi_aligned16(X) ||
       !rlvi_aligned16(weights) || (y && !rlvi_aligned16(y)))
@@ -415,6 +440,7 @@ int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const dou
   GramTmaParams p;
   p.y = y;
   p.w = weights;
+  p.center = center;
   p.n = n;
   p.d = d;
   p.power = power;
@@ -431,13 +457,16 @@ int rlvi_gram_tma_f64(rlvi_ctx* ctx, const double* X, const double* y, const dou
   int rc = rlvi_scratch(ctx, 4096 + size_t(units) * kUnitStride * sizeof(double), &scratch);
   if (rc != RLVI_OK) return rc;
   p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-  if (y) {
-    RLVI_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
-    gram_tma_kernel<true><<<int(units), kGThreads, kGSmem, st>>>(tmap, p);
-  } else {
-    RLVI_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem));
-    gram_tma_kernel<false><<<int(units), kGThreads, kGSmem, st>>>(tmap, p);
+#define RLVI_GRAM_TMA_LAUNCH(HY, CE)                                                                          \
+  {                                                                                                           \
+    RLVI_CUDA(cudaFuncSetAttribute(gram_tma_kernel<HY, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem)); \
+    gram_tma_kernel<HY, CE><<<int(units), kGThreads, kGSmem, st>>>(tmap, p);                                  \
   }
+  if (y && center) RLVI_GRAM_TMA_LAUNCH(true, true)
+  else if (y) RLVI_GRAM_TMA_LAUNCH(true, false)
+  else if (center) RLVI_GRAM_TMA_LAUNCH(false, true)
+  else RLVI_GRAM_TMA_LAUNCH(false, false)
+#undef RLVI_GRAM_TMA_LAUNCH
   RLVI_LAUNCH_CHECK(ctx);
   const int64_t total = int64_t(p.npairs) * kUnitStride;
   gram_tma_finalize_kernel<<<int((total + 255) / 256), 256, 0, st>>>(p.partials, int(nchunks), p.nb, p.npairs, d,

@@ -57,12 +57,13 @@ struct GramParams {
   const double* X;
   const double* y;
   const double* w;
+  const double* center;   // CENTERED: x_i is replaced by x_i - center
   int64_t n;
   int power;
   double* partials;   // [grid][kPartialStride]
 };
 
-template <bool HAS_Y>
+template <bool HAS_Y, bool CENTERED>
 __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -143,6 +144,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
     }
     const int g = lane >> 2, t = lane & 3;
     const int cidx = (g >> 1) | ((g & 1) << 2);
+    double cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cb[j] = CENTERED ? p.center[feat_of(j, g)] : 0.0;
     int stage = 0;
     uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -160,7 +164,11 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
         const double2 x1 = *reinterpret_cast<const double2*>(xr + 128);
         const double2 x2 = *reinterpret_cast<const double2*>(xr + 256);
         const double2 x3 = *reinterpret_cast<const double2*>(xr + 384);
-        const double b[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+        double b[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+        if (CENTERED) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] -= cb[j];
+        }
         const double w1 = sW[r];
         const double we = (p.power == 2) ? w1 * w1 : w1;
         double wy = 0.0;
@@ -296,6 +304,7 @@ struct ColParams {
   const double* y;
   const double* w;
   const double* params;   // logistic gradient: [b, theta(d)]
+  const double* center;   // MODE 0, optional: x_i - center
   int64_t n;
   int d;
   int power;
@@ -319,11 +328,13 @@ __global__ void __launch_bounds__(kColThreads) colsum_kernel(const ColParams p) 
     RowMap<FPL, VEC>::load_vec(smc + 1, p.d, q, L, th);
     __syncthreads();
   }
-  double a1[FPL], a2[FPL];
+  double a1[FPL], a2[FPL], cen[FPL];
 #pragma unroll
   for (int k = 0; k < FPL; ++k) {
     a1[k] = 0.0;
     a2[k] = 0.0;
+    const int f = RowMap<FPL, VEC>::feature(k, q, L);
+    cen[k] = (MODE == 0 && p.center && f < p.d) ? p.center[f] : 0.0;
   }
   double s0 = 0.0, swy = 0.0;
   const int64_t warps_total = int64_t(gridDim.x) * nwarp;
@@ -333,6 +344,10 @@ __global__ void __launch_bounds__(kColThreads) colsum_kernel(const ColParams p) 
     const bool valid = row < p.n;
     double x[FPL];
     RowMap<FPL, VEC>::load_row(p.X, row, p.d, q, L, valid, x);
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < FPL; ++k) x[k] -= cen[k];   // rows past n carry w = 0
+    }
     const double w1 = valid ? p.w[row] : 0.0;
     const double yi = (valid && p.y) ? p.y[row] : 0.0;
     double c1, c2 = 0.0;
@@ -419,6 +434,7 @@ constexpr int kGR = 16;   // rows per shared-memory step
 struct GenGramParams {
   const double* X;
   const double* w;
+  const double* center;
   int64_t n;
   int d;
   int power;
@@ -456,8 +472,8 @@ __global__ void __launch_bounds__(256) gen_gram_kernel(const GenGramParams p) {
         const double w1 = p.w[row];
         wa = (p.power == 2) ? w1 * w1 : w1;
         const int fa = bi * kGT + c, fb = bj * kGT + c;
-        if (fa < p.d) xa = p.X[row * int64_t(p.d) + fa];
-        if (fb < p.d) xb = p.X[row * int64_t(p.d) + fb];
+        if (fa < p.d) xa = p.X[row * int64_t(p.d) + fa] - (p.center ? p.center[fa] : 0.0);
+        if (fb < p.d) xb = p.X[row * int64_t(p.d) + fb] - (p.center ? p.center[fb] : 0.0);
       }
       As[r][c] = wa * xa;
       Bs[r][c] = xb;
@@ -549,6 +565,7 @@ struct ColTmaParams {
   const double* y;
   const double* w;
   const double* params;
+  const double* center;   // MODE 0, optional
   int64_t n;
   int d;
   int power;
@@ -626,6 +643,14 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
       a1[i] = 0.0;
       a2[i] = 0.0;
     }
+    double cen[2 * kMaxUnitsPerLane];
+#pragma unroll
+    for (int v = 0; v < kMaxUnitsPerLane; ++v) {
+      const int unit = lane + 32 * v;
+      const bool on = (MODE == 0) && p.center && unit < npair;
+      cen[2 * v] = on ? p.center[2 * unit] : 0.0;
+      cen[2 * v + 1] = on ? p.center[2 * unit + 1] : 0.0;
+    }
     double s0 = 0.0, swy = 0.0;
     for (int64_t t = warp; t < my_tiles; t += C) {
       const int64_t r = t / C;
@@ -682,7 +707,11 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
         for (int v = 0; v < kMaxUnitsPerLane; ++v) {
           const int unit = lane + 32 * v;
           if (unit < npair) {
-            const double2 x = xrow[unit];
+            double2 x = xrow[unit];
+            if (MODE == 0) {
+              x.x -= cen[2 * v];
+              x.y -= cen[2 * v + 1];
+            }
             a1[2 * v] = fma(k1, x.x, a1[2 * v]);
             a1[2 * v + 1] = fma(k1, x.y, a1[2 * v + 1]);
             if (MODE == 0) {
@@ -725,8 +754,8 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
 
 // shared host driver for the two colsum modes; result lands in out[0 .. 2+2d)
 template <int MODE>
-int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w, const double* params, int64_t n,
-               int d, int power, double* out, int count, cudaStream_t st) {
+int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w, const double* params,
+               const double* center, int64_t n, int d, int power, double* out, int count, cudaStream_t st) {
   // ---- TMA-fed path -------------------------------------------------------------------------------
   if (d % 16 == 0 && d <= 256 && n >= kCtRows && rlvi_aligned16(X) && rlvi_aligned16(w) && (!y || rlvi_aligned16(y))) {
     ColTmaParams q;
@@ -734,6 +763,7 @@ int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w,
     q.y = y;
     q.w = w;
     q.params = params;
+    q.center = center;
     q.n = n;
     q.d = d;
     q.power = power;
@@ -784,6 +814,7 @@ int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w,
   p.y = y;
   p.w = w;
   p.params = params;
+  p.center = center;
   p.n = n;
   p.d = d;
   p.power = power;
@@ -802,8 +833,25 @@ int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w,
 
 extern "C" int rlvi_moments_out_doubles(int d) { return 2 + 2 * d + d * d; }
 
+static int weighted_moments_impl(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
+                                 const double* center, int64_t n, int d, int power, int want_gram, double* out,
+                                 void* stream);
+
 extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
                                          int64_t n, int d, int power, int want_gram, double* out, void* stream) {
+  return weighted_moments_impl(ctx, X, y, weights, nullptr, n, d, power, want_gram, out, stream);
+}
+
+extern "C" int rlvi_weighted_moments_centered_f64(rlvi_ctx* ctx, const double* X, const double* y,
+                                                  const double* weights, const double* center, int64_t n, int d,
+                                                  int power, int want_gram, double* out, void* stream) {
+  RLVI_REQUIRE(center != nullptr, "null centre");
+  return weighted_moments_impl(ctx, X, y, weights, center, n, d, power, want_gram, out, stream);
+}
+
+static int weighted_moments_impl(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
+                                 const double* center, int64_t n, int d, int power, int want_gram, double* out,
+                                 void* stream) {
   RLVI_REQUIRE(ctx && X && weights && out, "null pointer");
   RLVI_REQUIRE(n > 0 && d > 0, "n and d must be positive");
   RLVI_REQUIRE(power == 1 || power == 2, "power must be 1 or 2");
@@ -825,13 +873,17 @@ extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const d
     p.n = n;
     p.power = power;
     p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-    if (y) {
-      RLVI_CUDA(cudaFuncSetAttribute(gram64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-      gram64_kernel<true><<<grid, kGramThreads, kGramSmem, st>>>(p);
-    } else {
-      RLVI_CUDA(cudaFuncSetAttribute(gram64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-      gram64_kernel<false><<<grid, kGramThreads, kGramSmem, st>>>(p);
-    }
+    p.center = center;
+#define RLVI_GRAM64_LAUNCH(HY, CE)                                                                              \
+  {                                                                                                             \
+    RLVI_CUDA(cudaFuncSetAttribute(gram64_kernel<HY, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem)); \
+    gram64_kernel<HY, CE><<<grid, kGramThreads, kGramSmem, st>>>(p);                                            \
+  }
+    if (y && center) RLVI_GRAM64_LAUNCH(true, true)
+    else if (y) RLVI_GRAM64_LAUNCH(true, false)
+    else if (center) RLVI_GRAM64_LAUNCH(false, true)
+    else RLVI_GRAM64_LAUNCH(false, false)
+#undef RLVI_GRAM64_LAUNCH
     RLVI_LAUNCH_CHECK(ctx);
     gram64_finalize_kernel<<<(4 * kPartialStride + 255) / 256, 256, 0, st>>>(p.partials, grid, want_gram, out);
     RLVI_LAUNCH_CHECK(ctx);
@@ -840,12 +892,12 @@ extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const d
 
   // ---- general d on the FP64 tensor pipe, TMA tensor-map fed (gram_tma.cu) --------------------------
   if (want_gram) {
-    const int trc = rlvi_gram_tma_f64(ctx, X, y, weights, n, d, power, want_gram, out, st);
+    const int trc = rlvi_gram_tma_f64(ctx, X, y, weights, center, n, d, power, want_gram, out, st);
     if (trc != RLVI_ERR_UNSUPPORTED) return trc;
   }
 
   // ---- fallback (odd d, unaligned pointers, tiny n): vectors first, then a register-tiled Gram ------
-  int rc = run_colsum<0>(ctx, X, y, weights, nullptr, n, d, power, out, 2 + 2 * d, st);
+  int rc = run_colsum<0>(ctx, X, y, weights, nullptr, center, n, d, power, out, 2 + 2 * d, st);
   if (rc != RLVI_OK) return rc;
   if (!want_gram) return RLVI_OK;
   if (d > 4096) {
@@ -855,6 +907,7 @@ extern "C" int rlvi_weighted_moments_f64(rlvi_ctx* ctx, const double* X, const d
   GenGramParams g;
   g.X = X;
   g.w = weights;
+  g.center = center;
   g.n = n;
   g.d = d;
   g.power = power;
@@ -888,5 +941,5 @@ extern "C" int rlvi_logistic_grad_f64(rlvi_ctx* ctx, const double* X, const doub
   RlviDeviceGuard guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // colsum MODE 1 leaves [sum c, -, X^T c (d), -] per CTA; the final sum gathers [sum c, X^T c]
-  return run_colsum<1>(ctx, X, y, weights, params, n, d, 1, out, 1 + d, st);
+  return run_colsum<1>(ctx, X, y, weights, params, nullptr, n, d, 1, out, 1 + d, st);
 }

@@ -153,9 +153,9 @@ def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=
     return losses_out, e_out, wsum_out
 
 
-def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None):
-    """rlvi_weighted_moments_f64.  Returns the flat device buffer [S0, Swy, S1(d), Sy(d), G(d*d)];
-    `split_moments` gives views."""
+def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, center=None):
+    """rlvi_weighted_moments_f64 (or, with `center`, rlvi_weighted_moments_centered_f64: x_i -> x_i - center).
+    Returns the flat device buffer [S0, Swy, S1(d), Sy(d), G(d*d)]; `split_moments` gives views."""
     dev = _dev(X)
     f64 = torch.float64
     _chk(X, f64, "X")
@@ -165,8 +165,15 @@ def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None):
     ctx = _lib.context(dev)
     if out is None:
         out = torch.zeros(ctx.lib.rlvi_moments_out_doubles(d), dtype=f64, device=X.device)
-    rc = ctx.lib.rlvi_weighted_moments_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
-                                           1 if want_gram else 0, _p(out), _stream(dev))
+    if center is None:
+        rc = ctx.lib.rlvi_weighted_moments_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
+                                               1 if want_gram else 0, _p(out), _stream(dev))
+    else:
+        _chk(center, f64, "center")
+        if center.numel() != d:
+            raise ValueError("center must have d elements")
+        rc = ctx.lib.rlvi_weighted_moments_centered_f64(ctx.handle, _p(X), _p(y), _p(weights), _p(center), n, d,
+                                                        int(power), 1 if want_gram else 0, _p(out), _stream(dev))
     _lib.check(rc, "rlvi_weighted_moments_f64")
     return out
 

@@ -186,15 +186,18 @@ def _gaussian_params(mu, cov):
 
 
 def covariance(samples, weights, mean=None):
-    """utils.py:92-108.  mu = X^T pi / sum pi; cov = (X-mu)^T Pi (X-mu) / sum pi (from one statistics pass:
-    G/S0 - mu mu^T); losses = Gaussian NLL.  The `mean` argument is ignored, as in the reference (line 103)."""
+    """utils.py:92-108.  mu = X^T pi / sum pi; cov = (X-mu)^T Pi (X-mu) / sum pi (a mean pass, then a centred
+    statistics pass, as the reference centres before the contraction); losses = Gaussian NLL.  The `mean`
+    argument is ignored, as in the reference (line 103)."""
     X, was_np = as_device(samples)
     wd, _ = as_device(weights, like=X)
     n, d = X.shape
-    mom = ops.weighted_moments(X, wd)
-    m = ops.split_moments(mom, d)
-    mu = m["S1"] / m["S0"]
-    cov = m["G"] / m["S0"] - torch.outer(mu, mu)
+    # pass 1: the weighted mean (utils.py:103); pass 2: statistics of the samples centred at it (utils.py:104-105)
+    m1 = ops.split_moments(ops.weighted_moments(X, wd, want_gram=False), d)
+    mu = (m1["S1"] / m1["S0"]).contiguous()
+    m = ops.split_moments(ops.weighted_moments(X, wd, center=mu), d)
+    delta = m["S1"] / m["S0"]                     # rounding-level residual of the centring
+    cov = m["G"] / m["S0"] - torch.outer(delta, delta)
     cov = 0.5 * (cov + cov.T)
     params = _gaussian_params(mu, cov)
     losses, _, _ = ops.loss(ops.LOSS_GAUSSIAN, X, params)

@@ -471,6 +471,28 @@ def test_covariance_golden(dev, tag):
     assert relmax(out, g["cov"]) < 1e-5       # bounded by Brent's accuracy in the constrained E-step (H4)
 
 
+@pytest.mark.parametrize("n,d", [(50, 2), (999, 3), (5000, 64), (3000, 128), (2000, 100)])
+def test_covariance_large_mean_is_centred(dev, n, d):
+    """The reference centres before the contraction (utils.py:103-105): a mean of 1e6 with unit variance must not
+    cost digits (G/S0 - mu mu^T would lose ~12)."""
+    from rlvi_b200 import ops, utils
+    rng = np.random.default_rng(n + d)
+    X = 1e6 + rng.normal(size=(n, d)) @ (np.eye(d) + 0.3 * rng.normal(size=(d, d)) / np.sqrt(d))
+    w = rng.random(n)
+    ref_cov, ref_losses = rlvi_np.covariance_mstep(X, w)
+    cov, losses = utils.covariance(X, w)
+    assert relmax(cov, ref_cov) < 1e-8          # limited by the reference's own rounding of x - mu at 1e6
+    assert relmax(losses, ref_losses) < 1e-6
+    # the centred statistics themselves, against NumPy on the same centre
+    c = X.mean(axis=0)
+    out = ops.weighted_moments(cu(X, dev), cu(w, dev), y=cu(w, dev), center=cu(c, dev))
+    m = {k: v.cpu().numpy() for k, v in ops.split_moments(out, d).items()}
+    Xc = X - c
+    assert relmax(m["G"], (Xc * w[:, None]).T @ Xc) < 1e-12
+    assert relmax(m["S1"], Xc.T @ w) < 1e-9
+    assert relmax(m["Sy"], Xc.T @ (w * w)) < 1e-9
+
+
 def test_covariance_singular_raises(dev):
     from rlvi_b200 import utils
     X = np.ones((20, 3))
