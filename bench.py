@@ -276,7 +276,7 @@ def run_b200(args):
 
     # ---- e2e: the same step through the host-buffer C-ABI call, H2D/D2H inside the timed region --------
     if not args.no_e2e:
-        line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total)
+        line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total, group)
     if world > 1:
         torch.distributed.barrier()
     del X, y
@@ -289,7 +289,7 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
-def run_e2e(args, X, y, params, dev, world, rank, n_total):
+def run_e2e(args, X, y, params, dev, world, rank, n_total, group):
     """Host buffers in, host buffers out: every step copies this rank's X/y shard host->device from pinned
     memory (inside rlvi_em_step_logistic_host), runs the three stages, and copies pi + statistics back."""
     import psutil
@@ -314,13 +314,19 @@ def run_e2e(args, X, y, params, dev, world, rank, n_total):
         # the host entry point is single-GPU (one shard per process); ranks run their shards side by side
         torch.distributed.barrier()
     steps = max(1, args.e2e_steps)
-    ops.em_step_logistic_host(Xh, yh, ph, pi_out=pih, device=dev.index)      # warm-up (allocates the resident copy)
+    if world > 1:     # every rank must run the same shard size for the global mean: agree on the smallest
+        t = torch.tensor([n_e2e], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        n_e2e = int(t)
+        Xh, yh, pih = Xh[:n_e2e], yh[:n_e2e], pih[:n_e2e]
+    kw = dict(pi_out=pih, device=dev.index, group=group, n_global=n_e2e * world)
+    ops.em_step_logistic_host(Xh, yh, ph, **kw)      # warm-up (allocates the resident copy)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        out = ops.em_step_logistic_host(Xh, yh, ph, pi_out=pih, device=dev.index)
+        out = ops.em_step_logistic_host(Xh, yh, ph, **kw)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     if world > 1:
@@ -334,7 +340,8 @@ def run_e2e(args, X, y, params, dev, world, rank, n_total):
             "note": "rlvi_em_step_logistic_host: pinned host X,y -> device (chunked, overlapped with the loss kernel), "
                     "E-step, statistics, pi + statistics -> host"
                     + ("" if n_e2e == n else f"; host RAM limited the e2e shard to {n_e2e} samples")
-                    + ("; N>1: independent shards, statistics not all-reduced in this call" if world > 1 else "")}
+                    + ("; N>1: rlvi_em_step_logistic_host_sharded -- global fixed point over NVLink peer windows, "
+                       "statistics all-reduced over the same windows" if world > 1 else "")}
 
 
 def main():

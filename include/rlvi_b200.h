@@ -231,6 +231,15 @@ int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, const double
                                const double* params_host, double tol, int maxiter, double* pi_host,
                                double* moments_host, rlvi_fp_result* result_host);
 
+/* The same step on THIS RANK'S SHARD of a sample-sharded data set (one process per GPU): the fixed point
+ * exchanges its sums with the peers inside the kernel (`fp_dist`, n_global = total samples), the statistics
+ * are all-reduced over the peer windows (`stats_dist`); both structs come from the same window with their own
+ * call_index sequences.  moments_host receives the GLOBAL statistics, pi_host this shard's posteriors. */
+int rlvi_em_step_logistic_host_sharded(rlvi_ctx* ctx, const double* X_host, const double* y_host, int64_t n, int d,
+                                       const double* params_host, double tol, int maxiter, double* pi_host,
+                                       double* moments_host, rlvi_fp_result* result_host,
+                                       const rlvi_fp_dist* fp_dist, const rlvi_fp_dist* stats_dist);
+
 #ifdef __cplusplus
 }
 #endif

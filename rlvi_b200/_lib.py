@@ -19,7 +19,7 @@ SYMBOLS = (
     "rlvi_fixed_point_deep_f32", "rlvi_shift_sum_f64", "rlvi_loss_f64", "rlvi_moments_out_doubles",
     "rlvi_weighted_moments_f64", "rlvi_weighted_moments_centered_f64", "rlvi_logistic_grad_f64", "rlvi_wce_fwd_bwd_f32", "rlvi_fn_threshold_f32",
     "rlvi_em_step_logistic_host", "rlvi_dist_window_create", "rlvi_dist_window_open", "rlvi_dist_window_close",
-    "rlvi_stats_allreduce_f64",
+    "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded",
 )
 
 FP_STANDARD, FP_ONLINE, FP_DEEP = 0, 1, 2
@@ -76,6 +76,8 @@ def load():
         lib.rlvi_wce_fwd_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp]
         lib.rlvi_fn_threshold_f32.argtypes = [vp, vp, i64, f32, f32, i32, vp, vp]
         lib.rlvi_em_step_logistic_host.argtypes = [vp, vp, vp, i64, i32, vp, f64, i32, vp, vp, C.POINTER(FpResult)]
+        lib.rlvi_em_step_logistic_host_sharded.argtypes = [vp, vp, vp, i64, i32, vp, f64, i32, vp, vp, C.POINTER(FpResult),
+                                                           C.POINTER(FpDist), C.POINTER(FpDist)]
         lib.rlvi_dist_window_create.argtypes = [vp, i32, C.POINTER(vp), C.c_char_p]
         lib.rlvi_dist_window_open.argtypes = [vp, i32, i32, vp, C.c_char_p, C.POINTER(vp)]
         lib.rlvi_dist_window_close.argtypes = [vp, i32, i32, vp, vp]

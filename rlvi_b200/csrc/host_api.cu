@@ -10,9 +10,33 @@ namespace {
 constexpr int64_t kChunkRows = int64_t(1) << 19;   // 256 MiB of X per chunk at d = 64
 }
 
+static int em_step_logistic_host_impl(rlvi_ctx* ctx, const double* X_host, const double* y_host, int64_t n, int d,
+                                      const double* params_host, double tol, int maxiter, double* pi_host,
+                                      double* moments_host, rlvi_fp_result* result_host, const rlvi_fp_dist* fp_dist,
+                                      const rlvi_fp_dist* stats_dist);
+
 extern "C" int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, const double* y_host, int64_t n,
                                           int d, const double* params_host, double tol, int maxiter,
                                           double* pi_host, double* moments_host, rlvi_fp_result* result_host) {
+  return em_step_logistic_host_impl(ctx, X_host, y_host, n, d, params_host, tol, maxiter, pi_host, moments_host,
+                                    result_host, nullptr, nullptr);
+}
+
+extern "C" int rlvi_em_step_logistic_host_sharded(rlvi_ctx* ctx, const double* X_host, const double* y_host,
+                                                  int64_t n, int d, const double* params_host, double tol,
+                                                  int maxiter, double* pi_host, double* moments_host,
+                                                  rlvi_fp_result* result_host, const rlvi_fp_dist* fp_dist,
+                                                  const rlvi_fp_dist* stats_dist) {
+  RLVI_REQUIRE(fp_dist && stats_dist, "null rlvi_fp_dist");
+  RLVI_REQUIRE(rlvi_moments_out_doubles(d) <= RLVI_DIST_STATS_CAPACITY, "statistics do not fit the peer window (d <= 88)");
+  return em_step_logistic_host_impl(ctx, X_host, y_host, n, d, params_host, tol, maxiter, pi_host, moments_host,
+                                    result_host, fp_dist, stats_dist);
+}
+
+static int em_step_logistic_host_impl(rlvi_ctx* ctx, const double* X_host, const double* y_host, int64_t n, int d,
+                                      const double* params_host, double tol, int maxiter, double* pi_host,
+                                      double* moments_host, rlvi_fp_result* result_host, const rlvi_fp_dist* fp_dist,
+                                      const rlvi_fp_dist* stats_dist) {
   RLVI_REQUIRE(ctx && X_host && y_host && params_host && moments_host && result_host, "null pointer");
   RLVI_REQUIRE(n > 0 && d > 0, "n and d must be positive");
   RlviDeviceGuard guard(ctx->device);
@@ -57,7 +81,7 @@ extern "C" int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, c
                            dE + r0, nullptr, ks);
     if (rc != RLVI_OK) return rc;
   }
-  int rc = rlvi_fixed_point_f64(ctx, RLVI_FP_STANDARD, nullptr, nullptr, dE, n, tol, maxiter, dPi, dRes, nullptr, ks);
+  int rc = rlvi_fixed_point_f64(ctx, RLVI_FP_STANDARD, nullptr, nullptr, dE, n, tol, maxiter, dPi, dRes, fp_dist, ks);
   if (rc != RLVI_OK) return rc;
   // pi goes back over PCIe on the copy stream while the statistics kernel runs on the compute stream
   if (pi_host) {
@@ -67,6 +91,10 @@ extern "C" int rlvi_em_step_logistic_host(rlvi_ctx* ctx, const double* X_host, c
   }
   rc = rlvi_weighted_moments_f64(ctx, dX, nullptr, dPi, n, d, 1, 1, dMom, ks);
   if (rc != RLVI_OK) return rc;
+  if (stats_dist) {   // sharded: the statistics of all ranks, same bits everywhere
+    rc = rlvi_stats_allreduce_f64(ctx, dMom, nm, stats_dist, ks);
+    if (rc != RLVI_OK) return rc;
+  }
   RLVI_CUDA(cudaMemcpyAsync(moments_host, dMom, size_t(nm) * 8, cudaMemcpyDeviceToHost, ks));
   RLVI_CUDA(cudaMemcpyAsync(result_host, dRes, sizeof(rlvi_fp_result), cudaMemcpyDeviceToHost, ks));
   RLVI_CUDA(cudaStreamSynchronize(ks));

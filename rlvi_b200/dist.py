@@ -89,6 +89,13 @@ class ShardGroup:
         self.calls += 1
         return _lib.FpDist(self.rank, self.world, int(n_global), self.window, self.table, self.calls)
 
+    def stats_dist(self):
+        """A fresh rlvi_fp_dist for the NEXT statistics all-reduce (its own call_index sequence)."""
+        if self.window is None:
+            raise RuntimeError("peer windows are only available on CUDA with world > 1")
+        self.stats_calls += 1
+        return _lib.FpDist(self.rank, self.world, 0, self.window, self.table, self.stats_calls)
+
     # ---- statistics ----------------------------------------------------------------------------
     STATS_CAPACITY = 8192     # RLVI_DIST_STATS_CAPACITY
 
@@ -101,8 +108,7 @@ class ShardGroup:
             return t
         if (self.window is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
                 and t.numel() <= self.STATS_CAPACITY):
-            self.stats_calls += 1
-            d = _lib.FpDist(self.rank, self.world, 0, self.window, self.table, self.stats_calls)
+            d = self.stats_dist()
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(self._ctx.lib.rlvi_stats_allreduce_f64(self._ctx.handle, C.c_void_p(t.data_ptr()), t.numel(),
                                                               C.byref(d), stream), "rlvi_stats_allreduce_f64")

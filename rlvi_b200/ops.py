@@ -243,7 +243,7 @@ def fn_threshold(weights, alpha=0.05, prev_threshold=0.0, truncate=False, *, out
 
 
 def em_step_logistic_host(X, y, params, *, tol=1e-3, maxiter=100, want_pi=True, device=0, pi_out=None,
-                          moments_out=None):
+                          moments_out=None, group=None, n_global=None):
     """rlvi_em_step_logistic_host on HOST arrays (NumPy or CPU torch tensors, FP64, C-contiguous; pinned
     memory makes the copies asynchronous).  Returns dict(pi, moments, result)."""
     def host_ptr(a, name):
@@ -273,9 +273,17 @@ def em_step_logistic_host(X, y, params, *, tol=1e-3, maxiter=100, want_pi=True, 
             return None
         return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
 
-    rc = ctx.lib.rlvi_em_step_logistic_host(ctx.handle, hx[0], hy[0], n, d, hp[0], float(tol), int(maxiter),
-                                            out_ptr(pi_out) if want_pi else None, out_ptr(moments_out),
-                                            C.byref(res))
+    if group is None or group.world == 1:
+        rc = ctx.lib.rlvi_em_step_logistic_host(ctx.handle, hx[0], hy[0], n, d, hp[0], float(tol), int(maxiter),
+                                                out_ptr(pi_out) if want_pi else None, out_ptr(moments_out),
+                                                C.byref(res))
+    else:      # this rank's shard of a sample-sharded data set (rlvi_b200.dist.ShardGroup)
+        fpd = group.fp_dist(int(n_global))
+        std = group.stats_dist()
+        rc = ctx.lib.rlvi_em_step_logistic_host_sharded(ctx.handle, hx[0], hy[0], n, d, hp[0], float(tol),
+                                                        int(maxiter), out_ptr(pi_out) if want_pi else None,
+                                                        out_ptr(moments_out), C.byref(res), C.byref(fpd),
+                                                        C.byref(std))
     _lib.check(rc, "rlvi_em_step_logistic_host")
     if res.iters < 0:
         raise _lib.RlviError("fixed-point kernel aborted: a grid barrier timed out")

@@ -41,6 +41,8 @@ def _worker(rank, world, port, n, d, q):
         g.all_reduce(mom)
         r = ops.read_result(res)
         out.append((r, pi.cpu().numpy(), mom.cpu().numpy()))
+    # the host-buffer entry point on this rank's shard (bench.py's e2e at N > 1)
+    host = ops.em_step_logistic_host(X[lo:hi], y[lo:hi], params, device=rank, group=g, n_global=n)
     # deep variant (FP32) sharded: min / max reductions cross the ranks too
     rng = np.random.default_rng(3)
     resid = rng.exponential(1.0, size=n).astype(np.float32) + 0.25
@@ -48,7 +50,7 @@ def _worker(rank, world, port, n, d, q):
     rt = torch.from_numpy(resid[lo:hi]).to(dev)
     wt = torch.from_numpy(w0[lo:hi]).to(dev)
     dres = ops.fixed_point_deep(rt, wt, dist=g.fp_dist(n))
-    q.put((rank, out, ops.read_result(dres), rt.cpu().numpy(), wt.cpu().numpy()))
+    q.put((rank, out, ops.read_result(dres), rt.cpu().numpy(), wt.cpu().numpy(), host))
     g.close()
     torch.distributed.destroy_process_group()
 
@@ -85,6 +87,14 @@ def test_sharded_em_step_matches_oracle(n):
         assert all(np.array_equal(m, moms[0]) for m in moms)
         G = moms[0][2 + 2 * d:].reshape(d, d)
         assert np.max(np.abs(G / moms[0][0] - ref["G"] / ref["S0"])) <= 1e-9 * np.max(np.abs(ref["G"] / ref["S0"]))
+    # sharded host-buffer step: global statistics on every rank, this shard's posteriors
+    hosts = [g[5] for g in got]
+    assert all(h["result"]["iters"] == ref["iters"] for h in hosts)
+    assert all(np.array_equal(h["moments"], hosts[0]["moments"]) for h in hosts)
+    Gh = hosts[0]["moments"][2 + 2 * d:].reshape(d, d)
+    assert np.max(np.abs(Gh / hosts[0]["moments"][0] - ref["G"] / ref["S0"])) <= 1e-9 * np.max(np.abs(ref["G"] / ref["S0"]))
+    pih = np.concatenate([h["pi"] for h in hosts])
+    assert np.max(np.abs(pih - ref["pi"])) <= tol * np.max(ref["pi"])
     # deep variant against the oracle on the unsharded vectors
     rng = np.random.default_rng(3)
     resid = torch.from_numpy(rng.exponential(1.0, size=n).astype(np.float32) + 0.25)
