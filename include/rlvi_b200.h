@@ -139,6 +139,12 @@ int rlvi_fixed_point_deep_f32(rlvi_ctx* ctx, float* residuals, float* weights, f
 int rlvi_shift_sum_f64(rlvi_ctx* ctx, const double* losses, int64_t n, double shift, double c,
                        double* pi_out, double* out_sum, void* stream);
 
+/* The same sum from e_i = exp(-l_i) (what rlvi_fixed_point_f64 leaves in `e_work`) and scale_t = exp(shift):
+ * t_i = e_i * scale_t.  No exp per sample: the 12-21 objective evaluations of one constrained E-step become
+ * HBM-bound passes.  Agrees with rlvi_shift_sum_f64 to rounding (exp(-l+s) vs exp(-l) exp(s)). */
+int rlvi_shift_sum_e_f64(rlvi_ctx* ctx, const double* e, int64_t n, double scale_t, double c, double* pi_out,
+                         double* out_sum, void* stream);
+
 /* ---- per-sample losses (one pass over X) ------------------------------------------------------ */
 enum rlvi_loss_kind {
   /* utils.py:19-21 cross_entropy: phi = b + x.theta;  l = -y phi + phi + log1p(exp(-phi)).

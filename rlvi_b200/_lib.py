@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librlvi_b200.so")
 SYMBOLS = (
     "rlvi_version", "rlvi_last_error", "rlvi_ctx_create", "rlvi_ctx_destroy", "rlvi_ctx_sm_count",
     "rlvi_ctx_launch_count", "rlvi_fp_dist_inbox_doubles", "rlvi_fixed_point_f64", "rlvi_fixed_point_init_f64",
-    "rlvi_fixed_point_deep_f32", "rlvi_shift_sum_f64", "rlvi_loss_f64", "rlvi_moments_out_doubles",
+    "rlvi_fixed_point_deep_f32", "rlvi_shift_sum_f64", "rlvi_shift_sum_e_f64", "rlvi_loss_f64", "rlvi_moments_out_doubles",
     "rlvi_weighted_moments_f64", "rlvi_weighted_moments_centered_f64", "rlvi_logistic_grad_f64", "rlvi_wce_fwd_bwd_f32", "rlvi_fn_threshold_f32",
     "rlvi_em_step_logistic_host", "rlvi_dist_window_create", "rlvi_dist_window_open", "rlvi_dist_window_close",
     "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded",
@@ -68,6 +68,7 @@ def load():
         lib.rlvi_fixed_point_init_f64.argtypes = [vp, i32, vp, vp, vp, i64, f64, i32, f64, vp, vp, C.POINTER(FpDist), vp]
         lib.rlvi_fixed_point_deep_f32.argtypes = [vp, vp, vp, vp, i64, f32, i32, vp, C.POINTER(FpDist), vp]
         lib.rlvi_shift_sum_f64.argtypes = [vp, vp, i64, f64, f64, vp, vp, vp]
+        lib.rlvi_shift_sum_e_f64.argtypes = [vp, vp, i64, f64, f64, vp, vp, vp]
         lib.rlvi_loss_f64.argtypes = [vp, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]
         lib.rlvi_moments_out_doubles.argtypes = [i32]
         lib.rlvi_weighted_moments_f64.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp]

@@ -288,6 +288,77 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const double* __restrict
   }
 }
 
+// Same objective from the precomputed e_i = exp(-l_i) the fixed point leaves behind:  t_i = e_i * exp(shift).
+// One reciprocal instead of an exp + a division per sample: the Brent search of rlvi.py:41 evaluates this
+// 12-21 times per E-step, each a full pass (HBM-bound here, FP64-bound with the exp).
+__device__ __forceinline__ double shift_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double t = fma(-x, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-x, r, 1.0);
+  return fma(r, t, r);
+}
+__global__ void __launch_bounds__(256) shift_sum_e_kernel(const double* __restrict__ e, int64_t n, double scale_t,
+                                                          double c, double* pi_out, double* partials,
+                                                          unsigned int* ticket, double* out_sum) {
+  __shared__ double s_red[8];
+  constexpr int U = 4;
+  const bool vec = ((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(pi_out)) & 15u) == 0;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  auto one = [&](double ev) {
+    const double t = ev * scale_t;
+    const double den = c + t;
+    // IEEE division where the weights are returned (rlvi.py:42), fast reciprocal for the objective only;
+    // den outside the normal range (t = inf, c + t = 0) takes the IEEE path too
+    const unsigned int ex = (unsigned int)(__double2hiint(den) >> 20) & 0x7ffu;
+    return (pi_out != nullptr || (ex - 123u) >= 1800u) ? t / den : t * shift_rcp(den);
+  };
+  if (vec) {
+    const double2* ev = reinterpret_cast<const double2*>(e);
+    double2* pv = reinterpret_cast<double2*>(pi_out);
+    const int64_t nvec = n >> 1;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i < nvec; i += U * stride) {
+      double2 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (i + u * stride < nvec) ? ev[i + u * stride] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i + u * stride < nvec) {
+          const double r0 = one(v[u].x), r1 = one(v[u].y);
+          acc0 += r0;
+          acc1 += r1;
+          if (pi_out) pv[i + u * stride] = make_double2(r0, r1);
+        }
+      }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const double r0 = one(e[n - 1]);
+      acc0 += r0;
+      if (pi_out) pi_out[n - 1] = r0;
+    }
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const double r0 = one(e[i]);
+      acc0 += r0;
+      if (pi_out) pi_out[i] = r0;
+    }
+  }
+  double v[1] = {acc0 + acc1};
+  block_sum<1>(v, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+  if (last_block_ticket(ticket, gridDim.x)) {
+    if (threadIdx.x < 32) {
+      double a = 0.0;
+      for (unsigned int j = threadIdx.x; j < gridDim.x; j += 32) a += partials[j];
+      a = warp_sum(a);
+      if (threadIdx.x == 0) out_sum[0] = a;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int rlvi_wce_fwd_bwd_f32(rlvi_ctx* ctx, const float* logits, const int64_t* labels,
@@ -369,6 +440,25 @@ extern "C" int rlvi_shift_sum_f64(rlvi_ctx* ctx, const double* losses, int64_t n
   if (rc != RLVI_OK) return rc;
   shift_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       losses, n, shift, c, pi_out, reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096),
+      reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128), out_sum);
+  RLVI_LAUNCH_CHECK(ctx);
+  return RLVI_OK;
+}
+
+extern "C" int rlvi_shift_sum_e_f64(rlvi_ctx* ctx, const double* e, int64_t n, double scale_t, double c, double* pi_out,
+                                    double* out_sum, void* stream) {
+  RLVI_REQUIRE(ctx && e && out_sum, "null pointer");
+  RLVI_REQUIRE(n > 0, "n must be positive");
+  RLVI_REQUIRE(scale_t >= 0.0 && scale_t < 1e300, "scale_t = exp(shift) must be finite and non-negative");
+  RlviDeviceGuard guard(ctx->device);
+  int64_t want = (n + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = int64_t(ctx->sm_count) * 8;
+  const int grid = int(want < 1 ? 1 : (want > cap ? cap : want));
+  void* scratch = nullptr;
+  int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * sizeof(double), &scratch);
+  if (rc != RLVI_OK) return rc;
+  shift_sum_e_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      e, n, scale_t, c, pi_out, reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096),
       reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128), out_sum);
   RLVI_LAUNCH_CHECK(ctx);
   return RLVI_OK;

@@ -461,6 +461,166 @@ __global__ void __launch_bounds__(kLossThreads) gaussian_loss_kernel(const Gauss
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed Gaussian NLL (d % 16 == 0, d <= 64, aligned): same producer / private-ring skeleton as
+// loss_tma_kernel; a consumer warp walks its 32-row tile as four 8-row DMMA groups, gathers the four groups'
+// quadratic forms so that lane l ends with row l (one shuffle per group), and then runs the exp tail and the
+// 256-byte stores with all 32 lanes.  (gaussian_loss_kernel above fetches its fragments straight from global
+// memory: latency-bound at 47 % of the DMMA peak.)
+// ---------------------------------------------------------------------------------------------
+struct GaussTmaParams {
+  const double* X;
+  const double* params;   // [c, mu(d), U(d*d) row-major upper triangular]
+  const double* w;
+  double* losses;
+  double* e_out;
+  double* wsum_out;
+  int64_t n;
+  int d;
+  int stage_bytes;
+  int ncons, depth;
+  double* partials;
+  unsigned int* ticket;
+};
+
+template <int NB>   // NB = d / 8 MMA blocks (exact)
+__global__ void __launch_bounds__(kTmaThreads, 1) gaussian_tma_kernel(const GaussTmaParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int D = NB * 8;
+  constexpr int kPitchU = D + 8;                 // doubles: conflict-free 128-bit reads of U rows
+  const int C = p.ncons, R = p.depth, S = C * R;
+  unsigned char* ring = smem_raw;
+  double* sU = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);   // D * kPitchU
+  double* sMu = sU + D * kPitchU;                                              // D
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sMu + D);
+  uint64_t* empty_bar = full_bar + kTmaMaxStages;
+  double* sRed = reinterpret_cast<double*>(empty_bar + kTmaMaxStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < D * kPitchU; i += blockDim.x) {
+    const int r = i / kPitchU, c = i - r * kPitchU;
+    sU[i] = (c < D && c >= r) ? p.params[1 + D + size_t(r) * D + c] : 0.0;
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sMu[i] = p.params[1 + i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double cst = p.params[0];
+  const int64_t ntiles = (p.n + kTmaRows - 1) / kTmaRows;
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(D) * 8u;
+  double s_wl = 0.0, s_w = 0.0;
+
+  if (warp == kTmaConsumers) {
+    if (lane < C) {
+      int64_t r = 0;
+      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
+        const int stage = lane * R + int(r % R);
+        const uint32_t phase = uint32_t(r / R) & 1u;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+        double* sW = reinterpret_cast<double*>(sX + tile_bytes);
+        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
+        if (row0 + kTmaRows <= p.n) {
+          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + (p.w ? 256u : 0u));
+          bulk_g2s(sX, p.X + row0 * D, tile_bytes, &full_bar[stage]);
+          if (p.w) bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
+        } else {
+          const int rows = int(p.n - row0);
+          for (int i = 0; i < rows; ++i) sW[i] = p.w ? p.w[row0 + i] : 0.0;
+          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(D) * 8u);
+          bulk_g2s(sX, p.X + row0 * D, uint32_t(rows) * uint32_t(D) * 8u, &full_bar[stage]);
+        }
+      }
+    }
+  } else if (warp < C) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int64_t tl = warp; tl < my_tiles; tl += C) {
+      const int64_t r = tl / C;
+      const int stage = warp * R + int(r % R);
+      const uint32_t phase = uint32_t(r / R) & 1u;
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
+      const double* sW = reinterpret_cast<const double*>(sX + tile_bytes);
+      double myquad = 0.0;
+#pragma unroll 1
+      for (int grp = 0; grp < 4; ++grp) {
+        // centred fragment of row 8 grp + g: features (8 kk + 2 t, + 1)
+        const double2* xrow = reinterpret_cast<const double2*>(sX + size_t(8 * grp + g) * D * 8);
+        double2 c[NB];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) {
+          double2 v = xrow[4 * kk + t];
+          const double2 m = *reinterpret_cast<const double2*>(sMu + 8 * kk + 2 * t);
+          v.x -= m.x;
+          v.y -= m.y;
+          c[kk] = v;
+        }
+        double quad = 0.0;
+#pragma unroll
+        for (int nbk = 0; nbk < NB; ++nbk) {
+          double z0 = 0.0, z1 = 0.0;
+          const double* urow = sU + size_t(8 * nbk + g) * kPitchU + 2 * t;
+#pragma unroll
+          for (int kk = nbk; kk < NB; ++kk) {
+            const double2 u = *reinterpret_cast<const double2*>(urow + 8 * kk);
+            dmma884(z0, z1, c[kk].x, u.x);
+            dmma884(z0, z1, c[kk].y, u.y);
+          }
+          quad = fma(z0, z0, quad);
+          quad = fma(z1, z1, quad);
+        }
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        // row 8 grp + g's form sits in lanes 4 g .. 4 g + 3; lane l wants row l
+        const double got = __shfl_sync(0xffffffffu, quad, 4 * (lane & 7));
+        if ((lane >> 3) == grp) myquad = got;
+      }
+      const double wi = sW[lane];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      const int64_t row = (blockIdx.x + tl * gridDim.x) * kTmaRows + lane;
+      if (row < p.n) {
+        const double loss = 0.5 * (myquad + cst);                    // utils.py:101
+        if (p.losses) p.losses[row] = loss;
+        if (p.e_out) p.e_out[row] = exp(-loss);
+        if (p.w) {
+          s_wl = fma(wi, loss, s_wl);
+          s_w += wi;
+        }
+      }
+    }
+  }
+
+  if (p.w) {
+    double v[2] = {s_wl, s_w};
+    block_sum<2>(v, sRed);
+    if (threadIdx.x == 0) {
+      p.partials[2 * blockIdx.x] = v[0];
+      p.partials[2 * blockIdx.x + 1] = v[1];
+    }
+    if (last_block_ticket(p.ticket, gridDim.x)) {
+      if (threadIdx.x < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (unsigned int j = lane; j < gridDim.x; j += 32) {
+          a0 += p.partials[2 * j];
+          a1 += p.partials[2 * j + 1];
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+          p.wsum_out[0] = a0;
+          p.wsum_out[1] = a1;
+        }
+      }
+    }
+  }
+}
+
 template <int DOTK>
 int launch_loss(rlvi_ctx* ctx, const RowMapCfg& cfg, LossParams& p, int grid, size_t smem, cudaStream_t st) {
 #define RLVI_LOSS_CASE(F, V)                                                            \
@@ -500,6 +660,44 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
     if (d > 128) {
       rlvi_set_error("RLVI_LOSS_GAUSSIAN supports d <= 128 (got %d)", d);
       return RLVI_ERR_UNSUPPORTED;
+    }
+    // ---- TMA-fed path: d in {16, 32, 48, 64}, aligned, at least one full tile ------------------------
+    if (d % 16 == 0 && d <= 64 && n >= kTmaRows && rlvi_aligned16(X) && (!weights || rlvi_aligned16(weights))) {
+      GaussTmaParams q;
+      q.X = X;
+      q.params = params;
+      q.w = weights;
+      q.losses = losses_out;
+      q.e_out = e_out;
+      q.wsum_out = wsum_out;
+      q.n = n;
+      q.d = d;
+      q.stage_bytes = kTmaRows * d * 8 + 256;
+      const size_t tail = (size_t(d) * (d + 8) + d) * 8 + 2 * kTmaMaxStages * 8 + 2 * (kTmaConsumers + 1) * 8 + 128;
+      const int max_stages = int((size_t(220) * 1024 - tail) / q.stage_bytes);
+      q.ncons = max_stages < kTmaConsumers ? max_stages : kTmaConsumers;
+      q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
+      if (q.depth > 2) q.depth = 2;
+      const int64_t ntiles = (n + kTmaRows - 1) / kTmaRows;
+      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
+      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+      int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * 2 * sizeof(double), &scratch);
+      if (rc != RLVI_OK) return rc;
+      q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
+      q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
+      const size_t smem = size_t(q.ncons) * q.depth * q.stage_bytes + tail;
+#define RLVI_GTMA_CASE(NB)                                                                                    \
+  if (d == 8 * NB) {                                                                                          \
+    RLVI_CUDA(cudaFuncSetAttribute(gaussian_tma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    gaussian_tma_kernel<NB><<<grid, kTmaThreads, smem, st>>>(q);                                              \
+    RLVI_LAUNCH_CHECK(ctx);                                                                                   \
+    return RLVI_OK;                                                                                           \
+  }
+      RLVI_GTMA_CASE(2)
+      RLVI_GTMA_CASE(4)
+      RLVI_GTMA_CASE(6)
+      RLVI_GTMA_CASE(8)
+#undef RLVI_GTMA_CASE
     }
     const int nb = (d + 7) / 8, dp = nb * 8;
     const size_t smem = (size_t(dp) * (dp + 8) + dp + 2 * warps_per_block) * sizeof(double);

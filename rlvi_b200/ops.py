@@ -16,7 +16,7 @@ from ._lib import (FP_DEEP, FP_ONLINE, FP_STANDARD, LOSS_GAUSSIAN, LOSS_LOGISTIC
                    LOSS_SQDIST, LOSS_SQRES)
 
 __all__ = ["FP_STANDARD", "FP_ONLINE", "FP_DEEP", "LOSS_LOGISTIC_CE", "LOSS_SOFTPLUS", "LOSS_SQRES",
-           "LOSS_SQDIST", "LOSS_PCA", "LOSS_GAUSSIAN", "fixed_point", "fixed_point_deep", "shift_sum", "loss",
+           "LOSS_SQDIST", "LOSS_PCA", "LOSS_GAUSSIAN", "fixed_point", "fixed_point_deep", "shift_sum", "shift_sum_e", "loss",
            "weighted_moments", "split_moments", "logistic_grad", "wce_fwd_bwd", "fn_threshold", "read_result",
            "em_step_logistic_host", "launch_count"]
 
@@ -125,6 +125,20 @@ def shift_sum(losses, shift, c, *, pi_out=None, out=None):
     rc = ctx.lib.rlvi_shift_sum_f64(ctx.handle, _p(losses), losses.numel(), float(shift), float(c), _p(pi_out),
                                     _p(out), _stream(dev))
     _lib.check(rc, "rlvi_shift_sum_f64")
+    return out
+
+
+def shift_sum_e(e, scale_t, c, *, pi_out=None, out=None):
+    """rlvi_shift_sum_e_f64: out[0] = sum_i t_i/(c+t_i), t_i = e_i * scale_t (e = exp(-l), scale_t = exp(shift))."""
+    dev = _dev(e)
+    _chk(e, torch.float64, "e")
+    _chk(pi_out, torch.float64, "pi_out")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=e.device)
+    ctx = _lib.context(dev)
+    rc = ctx.lib.rlvi_shift_sum_e_f64(ctx.handle, _p(e), e.numel(), float(scale_t), float(c), _p(pi_out), _p(out),
+                                      _stream(dev))
+    _lib.check(rc, "rlvi_shift_sum_e_f64")
     return out
 
 

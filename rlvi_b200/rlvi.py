@@ -18,6 +18,8 @@ There is no CPU fallback.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 from scipy import optimize as _opt
@@ -46,18 +48,27 @@ def update_weights_constrained(losses, n_eff, tol=1e-3, maxiter=100):
     (SURVEY.md H4)."""
     l, was_np = as_device(losses)
     n = l.numel()
-    pi, res = ops.fixed_point(l, variant=ops.FP_STANDARD, tol=tol, maxiter=maxiter)
-    sum_pi = pi.sum().item()                                    # rlvi.py:32  np.sum(weights) < n_eff
+    e = torch.empty_like(l)
+    pi, res = ops.fixed_point(l, e_work=e, variant=ops.FP_STANDARD, tol=tol, maxiter=maxiter)
+    sum_pi = ops.read_result(res)["sum_pi"]                      # rlvi.py:32  np.sum(weights) < n_eff
     if sum_pi < n_eff:
         c = (n - n_eff) / n_eff
         acc = torch.empty(1, dtype=torch.float64, device=l.device)
 
+        def shift_sum(s, pi_out=None):
+            # exp(-l + s) = e * exp(s): the fixed point already left e = exp(-l) behind, so an evaluation is one
+            # exp-free pass; outside exp's comfortable range fall back to the literal expression
+            if -600.0 < s < 600.0:
+                ops.shift_sum_e(e, math.exp(s), c, pi_out=pi_out, out=acc)
+            else:
+                ops.shift_sum(l, s, c, pi_out=pi_out, out=acc)
+            return acc.item()
+
         def shift_obj(s):                                        # rlvi.py:34-39
-            ops.shift_sum(l, s, c, out=acc)
-            return np.square(acc.item() - n_eff)
+            return np.square(shift_sum(s) - n_eff)
 
         shift = _opt.minimize_scalar(shift_obj)["x"]             # rlvi.py:41
-        ops.shift_sum(l, shift, c, pi_out=pi, out=acc)           # rlvi.py:42
+        shift_sum(shift, pi_out=pi)                              # rlvi.py:42
     return to_caller(pi, was_np)
 
 

@@ -208,6 +208,16 @@ def test_shift_sum(dev):
     out = ops.shift_sum(cu(l, dev), s, c, pi_out=pi)
     assert abs(out.item() - ref.sum()) < 1e-12 * ref.sum()
     assert relmax(pi.cpu().numpy(), ref) < 1e-14
+    # the exp-free form on e = exp(-l): objective only (fast reciprocal) and with the weights (IEEE division)
+    e = cu(np.exp(-l), dev)
+    for off in (0, 1):                                           # aligned (vector) and unaligned (scalar) paths
+        ev = torch.cat([torch.zeros(off, dtype=torch.float64, device=dev), e])[off:]
+        out2 = ops.shift_sum_e(ev, np.exp(s), c)
+        assert abs(out2.item() - ref.sum()) < 1e-12 * ref.sum()
+        pi2 = torch.empty(l.size + off, dtype=torch.float64, device=dev)[off:]
+        out3 = ops.shift_sum_e(ev, np.exp(s), c, pi_out=pi2)
+        assert abs(out3.item() - ref.sum()) < 1e-12 * ref.sum()
+        assert relmax(pi2.cpu().numpy(), ref) < 1e-14
 
 
 # ==================================================================================================
@@ -292,7 +302,8 @@ def test_losses_unaligned_rows(dev):
     assert np.max(np.abs(l.cpu().numpy() - ref)) < 1e-11 * np.max(np.sum(X ** 2, axis=1))
 
 
-@pytest.mark.parametrize("n,d", [(50, 2), (999, 3), (2048, 16), (1500, 64), (700, 65), (300, 128)])
+@pytest.mark.parametrize("n,d", [(50, 2), (999, 3), (2048, 16), (1500, 64), (700, 65), (300, 128), (300001, 64),
+                                 (100000, 32), (70001, 48), (33, 16)])
 def test_gaussian_loss_against_oracle(dev, n, d):
     from rlvi_b200 import ops, utils
     rng = np.random.default_rng(d)

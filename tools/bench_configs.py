@@ -62,6 +62,32 @@ def config3():
          loss_ms=t_loss, loss_GBps=n * (d + 1) * 8 / t_loss / 1e6, torch_cublas_gram_ms=t_blas)
 
 
+def config2_covariance():
+    """configs[1], second model: covariance estimation at d = 64 (utils.covariance + constrained E-step pieces)."""
+    n, d = 1 << 24, 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.randn((n, d), generator=g, device=dev, dtype=torch.float64) * 0.25
+    w = torch.rand(n, generator=g, device=dev, dtype=torch.float64)
+    mu = torch.zeros(d, dtype=torch.float64, device=dev)
+    cov = torch.eye(d, dtype=torch.float64, device=dev) * 0.0625
+    params = utils._gaussian_params(mu, cov)
+    losses = torch.empty(n, dtype=torch.float64, device=dev)
+    t_loss = timeit(lambda: ops.loss(ops.LOSS_GAUSSIAN, X, params, losses_out=losses), reps=5)
+    t_mean = timeit(lambda: ops.weighted_moments(X, w, want_gram=False), reps=5)
+    t_gram = timeit(lambda: ops.weighted_moments(X, w, center=mu), reps=5)
+    acc = torch.empty(1, dtype=torch.float64, device=dev)
+    t_shift = timeit(lambda: ops.shift_sum(losses, 0.3, 0.4, out=acc), reps=5)
+    e = torch.exp(-losses)
+    t_shift_e = timeit(lambda: ops.shift_sum_e(e, 1.35, 0.4, out=acc), reps=5)
+    t_fp = timeit(lambda: ops.fixed_point(losses), reps=3)
+    emit(config="2b: covariance model pieces, FP64, N=2^24, d=64", gaussian_loss_ms=t_loss,
+         gaussian_loss_GBps=n * (d + 1) * 8 / t_loss / 1e6, gaussian_loss_tflops=n * 72 * 512 / 8 / t_loss / 1e9,
+         mean_pass_ms=t_mean, mean_pass_GBps=n * (d + 1) * 8 / t_mean / 1e6, centred_gram_ms=t_gram,
+         shift_sum_ms=t_shift, shift_sum_GBps=n * 8 / t_shift / 1e6, shift_sum_e_ms=t_shift_e,
+         shift_sum_e_GBps=n * 8 / t_shift_e / 1e6, fixed_point_ms=t_fp)
+    del X, w, losses
+
+
 def config4():
     rng = np.random.default_rng(1)
     losses = torch.from_numpy(rng.exponential(0.7, size=100)).to(dev)
@@ -134,6 +160,7 @@ def loops():
 
 
 if __name__ == "__main__":
+    config2_covariance()
     config5()
     config4()
     config3()
