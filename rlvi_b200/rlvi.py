@@ -121,9 +121,12 @@ def mean(sample, maxiter=100, tol=1e-3):
 def _gpu_sym_solve(G, b):
     """theta = argmin ||sqrt(Pi) (X theta - y)||.  The reference calls scipy lstsq (LAPACK gelsd) on the
     N x d scaled design (rlvi.py:71,80); this is the same minimiser from the d x d statistics
-    G = X^T Pi X, b = X^T Pi y, through an eigen-decomposition pseudo-inverse so that rank-deficient
-    designs give the minimum-norm solution as gelsd does."""
-    evals, evecs = torch.linalg.eigh(G)
+    G = X^T Pi X, b = X^T Pi y: Cholesky when G is positive definite, else an eigen-decomposition
+    pseudo-inverse so that rank-deficient designs give the minimum-norm solution as gelsd does."""
+    L, info = torch.linalg.cholesky_ex(G)
+    if int(info) == 0:                       # the usual case: G is positive definite
+        return torch.cholesky_solve(b.unsqueeze(1), L)[:, 0]
+    evals, evecs = torch.linalg.eigh(G)      # rank-deficient design: minimum-norm solution, gelsd's rcond rule
     cutoff = torch.finfo(G.dtype).eps * evals.abs().max()
     inv = torch.where(evals.abs() > cutoff, 1.0 / evals, torch.zeros_like(evals))
     return evecs @ (inv * (evecs.T @ b))
