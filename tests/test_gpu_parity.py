@@ -160,6 +160,19 @@ def test_online_carry_over_extension(dev):
     assert relmax(w2, rlvi_np.update_weights_online(l2)) > 1e-6      # really different from the 0.5 restart
 
 
+def test_c_abi_from_c(dev):
+    """The C ABI driven from a plain C++ program (CUDA runtime only, no Python / torch on that side), checked
+    against a scalar restatement of the reference arithmetic written in C (tests/c_abi/abi_smoke.cu)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c_abi", "abi_smoke")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    for n in ("50000", "1031"):
+        r = subprocess.run([exe, n], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "C-ABI PARITY OK" in r.stdout
+
+
 def test_c_abi_error_codes(dev):
     """Bad arguments come back as negative codes + message (never a crash, never a silent fallback)."""
     from rlvi_b200 import _lib, ops
