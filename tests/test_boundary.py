@@ -52,6 +52,42 @@ def test_library_loads_and_host_only_calls_work(built):
     assert isinstance(lib.rlvi_last_error(), bytes)
 
 
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of the two public structs as gcc sees the header == the ctypes mirrors in _lib.py."""
+    import ctypes as C
+    from rlvi_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "rlvi_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rlvi_fp_result), offsetof(rlvi_fp_result, eps),\n'
+        '         offsetof(rlvi_fp_result, rho), offsetof(rlvi_fp_result, sum_pi), offsetof(rlvi_fp_result, err),\n'
+        '         offsetof(rlvi_fp_result, iters), offsetof(rlvi_fp_result, converged));\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rlvi_fp_dist), offsetof(rlvi_fp_dist, rank),\n'
+        '         offsetof(rlvi_fp_dist, world), offsetof(rlvi_fp_dist, n_global), offsetof(rlvi_fp_dist, inbox),\n'
+        '         offsetof(rlvi_fp_dist, peer_inbox), offsetof(rlvi_fp_dist, call_index));\n'
+        '  printf("%d %d\\n", RLVI_IPC_HANDLE_BYTES, RLVI_DIST_STATS_CAPACITY);\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    res = [int(v) for v in out[0].split()]
+    dist = [int(v) for v in out[1].split()]
+    R, D = _lib.FpResult, _lib.FpDist
+    assert res == [C.sizeof(R)] + [getattr(R, f).offset for f in ("eps", "rho", "sum_pi", "err", "iters", "converged")]
+    assert dist == [C.sizeof(D)] + [getattr(D, f).offset for f in ("rank", "world", "n_global", "inbox", "peer_inbox",
+                                                                   "call_index")]
+    from rlvi_b200.dist import ShardGroup
+    assert [int(v) for v in out[2].split()] == [64, ShardGroup.STATS_CAPACITY]
+
+
+def test_header_is_plain_c(tmp_path):
+    """The header compiles as C99 (no C++-isms, no CUDA or torch types in the signatures)."""
+    src = tmp_path / "inc.c"
+    src.write_text('#include "rlvi_b200.h"\nint main(void) { return rlvi_version() < 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(tmp_path / "inc.o")], check=True)
+
+
 def test_library_is_sm100a_only(built):
     out = subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))

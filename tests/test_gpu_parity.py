@@ -166,7 +166,9 @@ def test_c_abi_from_c(dev):
     import os
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c_abi", "abi_smoke")
-    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    if not os.path.exists(exe):                 # normally built by __graft_entry__.build() and shipped in-tree
+        import __graft_entry__ as g
+        g.build()
     for n in ("50000", "1031"):
         r = subprocess.run([exe, n], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stdout + r.stderr
