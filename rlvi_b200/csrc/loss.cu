@@ -14,7 +14,7 @@
 #include <math.h>
 
 #include "rowmap.cuh"
-#include "tma.cuh"
+#include "tma_ring.cuh"
 
 namespace {
 
@@ -144,26 +144,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
 
 // ---------------------------------------------------------------------------------------------
 // TMA-fed streaming kernel (d % 16 == 0, d <= 256, 16-byte aligned pointers): the headline path.
-//   * persistent, one CTA per SM: 16 consumer warps + 1 producer warp;
-//   * the producer streams 32-row tiles into an S-stage shared-memory ring: ONE cp.async.bulk (TMA engine,
-//     SASS UBLKCP) of 32*d*8 contiguous bytes of X per tile, plus 256 bytes of y and of pi, completing on
-//     an mbarrier.  (A first version issued one 512-byte copy per row into a padded pitch: the serialised
-//     per-row UBLKCP issue, ~67 clk per row, capped the kernel at 2.3 TB/s.)
-//   * tile t of the CTA is consumed by warp t mod C (C <= 16 consumer warps, each with a private ring of
-//     R stages; C*R stages fill the shared memory): lane l owns row l of the tile and does the whole
-//     d-long dot product itself.  Rows sit at their natural d*8-byte pitch (a multiple of 128 bytes), so
-//     lane l walks its row ROTATED by l 16-byte units -- unit (j + l) mod (d/2) at step j -- which makes
-//     every 128-bit shared-memory read of x and of theta bank-conflict free;
-//   * the exp / log1p tail then runs with ALL 32 lanes busy (the register-tiled kernel above leaves 3/4
-//     of the lanes idle there and exposes the global-load latency once per row group);
-//   * outputs are one coalesced 256-byte store per warp and array.
+// Producer / private-ring skeleton: tma_ring.cuh.  Consumer: lane l owns row l of its warp's 32-row tile and
+// does the whole d-long dot product itself.  Rows sit at their natural d*8-byte pitch (a multiple of 128
+// bytes), so lane l walks its row ROTATED by l 16-byte units -- unit (j + l) mod (d/2) at step j -- which
+// makes every 128-bit shared-memory read of x and of theta bank-conflict free; the exp / log1p tail then runs
+// with ALL 32 lanes busy (the register-tiled kernel above leaves 3/4 of the lanes idle there and exposes the
+// global-load latency once per row group); outputs are one coalesced 256-byte store per warp and array.
 // Algorithmic bytes per sample: d*8 (X) + 8 (y) [+ 8 (pi)] in, 8 (l) and/or 8 (e) out.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTmaConsumers = 16;
-constexpr int kTmaThreads = (kTmaConsumers + 1) * 32;
-constexpr int kTmaRows = 32;
-constexpr int kTmaMaxStages = 2 * kTmaConsumers;
-
 struct LossTmaParams {
   const double* X;
   const double* y;
@@ -176,91 +164,44 @@ struct LossTmaParams {
   int d;
   int kind;
   int intercept;
-  int stage_bytes;    // kTmaRows * d * 8 + 512 (y, pi)
-  int ncons;          // consumer warps in use (<= kTmaConsumers)
-  int depth;          // ring stages per consumer warp; nstages = ncons * depth
-  int nstages;
+  RingGeom geom;
   double* partials;   // [grid][2]
   unsigned int* ticket;
 };
 
+// shared-memory tail after the ring: theta (d doubles, padded), the barriers, the block-reduction scratch
+static inline size_t loss_tma_tail(int d) {
+  return size_t(((d + 1) & ~1) + 2) * 8 + kRingBarrierBytes + 2 * (kRingConsumers + 1) * 8 + 128;
+}
+
 template <int DOTK>
-__global__ void __launch_bounds__(kTmaThreads, 1) loss_tma_kernel(const LossTmaParams p) {
+__global__ void __launch_bounds__(kRingThreads, 1) loss_tma_kernel(const LossTmaParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int S = p.nstages, C = p.ncons, R = p.depth;
-  unsigned char* ring = smem_raw;
-  double* sTheta = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);      // d (+ pad to even)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sTheta + ((p.d + 1) & ~1) + 2);
-  uint64_t* empty_bar = full_bar + kTmaMaxStages;
-  double* sRed = reinterpret_cast<double*>(empty_bar + kTmaMaxStages);               // 2 * 17 doubles
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = p.d;
+  Ring ring;
+  ring.base = smem_raw;
+  ring.g = p.geom;
+  ring.d = d;
+  double* sTheta = reinterpret_cast<double*>(smem_raw + ring_bytes(p.geom));         // d (+ pad to even)
+  ring.full_bar = reinterpret_cast<uint64_t*>(sTheta + ((d + 1) & ~1) + 2);
+  ring.empty_bar = ring.full_bar + kRingMaxStages;
+  double* sRed = reinterpret_cast<double*>(ring.empty_bar + kRingMaxStages);          // 2 * 17 doubles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < d; i += blockDim.x) sTheta[i] = p.params[i + (p.intercept ? 1 : 0)];
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  ring_init(ring);
   const double b0 = p.intercept ? p.params[0] : 0.0;
-  const int64_t ntiles = (p.n + kTmaRows - 1) / kTmaRows;
-  // tiles of this CTA: blockIdx.x, blockIdx.x + grid, ...   local index t -> stage t % S, warp t % 8
-  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = ring_my_tiles(p.n);
   const bool need_y = (p.kind == RLVI_LOSS_LOGISTIC_CE || p.kind == RLVI_LOSS_SQRES);
   double s_wl = 0.0, s_w = 0.0;
 
-  if (warp == kTmaConsumers) {
-    // ===== producer warp =========================================================================
-    // Lane c of the producer warp feeds consumer warp c (its private ring of R stages), so a slow consumer
-    // never blocks the refills of the others.  Stage ownership is static: the r-th tile of consumer c is
-    // local tile c + r C and lives in stage c R + r % R.  (Letting successive uses of one stage go to
-    // different warps is unsafe: a warp could wait for phase k+1 of a barrier still in phase k, which
-    // mbarrier.try_wait.parity reports as complete.)
-    const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(d) * 8u;
-    if (lane < C) {
-      int64_t r = 0;
-      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
-        const int stage = lane * R + int(r % R);
-        const uint32_t phase = uint32_t(r / R) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-        double* sY = reinterpret_cast<double*>(sX + tile_bytes);
-        double* sW = sY + kTmaRows;
-        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
-        if (row0 + kTmaRows <= p.n) {
-          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + (need_y ? 256u : 0u) + (p.w ? 256u : 0u));
-          bulk_g2s(sX, p.X + row0 * d, tile_bytes, &full_bar[stage]);
-          if (need_y) bulk_g2s(sY, p.y + row0, 256, &full_bar[stage]);
-          if (p.w) bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
-        } else {
-          // ragged last tile: X rows by one (shorter) bulk copy, y / pi by plain stores that the
-          // release semantics of the arrive below publish (rows past n are never read back)
-          const int rows = int(p.n - row0);
-          for (int i = 0; i < rows; ++i) {
-            sY[i] = need_y ? p.y[row0 + i] : 0.0;
-            sW[i] = p.w ? p.w[row0 + i] : 0.0;
-          }
-          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(d) * 8u);
-          bulk_g2s(sX, p.X + row0 * d, uint32_t(rows) * uint32_t(d) * 8u, &full_bar[stage]);
-        }
-      }
-    }
-  } else if (warp < C) {
-    // ===== consumer warps ========================================================================
+  if (warp == kRingConsumers) {
+    ring_produce(ring, p.X, need_y ? p.y : nullptr, p.w, p.n, my_tiles, false);
+  } else if (warp < p.geom.ncons) {
     const double2* th2 = reinterpret_cast<const double2*>(sTheta);
     const int npair = d >> 1;                      // 16-byte units per row, a multiple of 8
-    const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(d) * 8u;
-    for (int64_t t = warp; t < my_tiles; t += C) {
-      const int64_t r = t / C;
-      const int stage = warp * R + int(r % R);
-      const uint32_t phase = uint32_t(r / R) & 1u;
-      mbar_wait(&full_bar[stage], phase);
-      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-      const double* sY = reinterpret_cast<const double*>(sX + tile_bytes);
-      const double* sW = sY + kTmaRows;
-      const double2* xr = reinterpret_cast<const double2*>(sX) + size_t(lane) * npair;
+    for (int64_t t = warp; t < my_tiles; t += p.geom.ncons) {
+      const RingStage st = ring_acquire(ring, warp, t);
+      const double2* xr = reinterpret_cast<const double2*>(st.x) + size_t(lane) * npair;
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, q0 = 0.0, q1 = 0.0;
       int u = lane % npair;                         // rotated walk: conflict-free at the natural pitch
 #pragma unroll 4
@@ -292,11 +233,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) loss_tma_kernel(const LossTmaP
       }
       const double a = (a0 + a1) + (a2 + a3);
       const double b = q0 + q1;
-      const double yi = sY[lane];
-      const double wi = sW[lane];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);      // the stage can be refilled while we do the tail
-      const int64_t row = (blockIdx.x + t * gridDim.x) * kTmaRows + lane;
+      const double yi = st.y[lane];
+      const double wi = st.w[lane];
+      ring_release(ring, st);                        // the stage can be refilled while we do the tail
+      const int64_t row = ring_row0(t) + lane;
       if (row < p.n) {
         const double loss = finish_loss(p.kind, a, b, b0, need_y ? yi : 0.0);
         if (p.losses) p.losses[row] = loss;
@@ -477,80 +417,51 @@ struct GaussTmaParams {
   double* wsum_out;
   int64_t n;
   int d;
-  int stage_bytes;
-  int ncons, depth;
+  RingGeom geom;
   double* partials;
   unsigned int* ticket;
 };
 
+static inline size_t gauss_tma_tail(int d) {
+  return (size_t(d) * (d + 8) + d) * 8 + kRingBarrierBytes + 2 * (kRingConsumers + 1) * 8 + 128;
+}
+
 template <int NB>   // NB = d / 8 MMA blocks (exact)
-__global__ void __launch_bounds__(kTmaThreads, 1) gaussian_tma_kernel(const GaussTmaParams p) {
+__global__ void __launch_bounds__(kRingThreads, 1) gaussian_tma_kernel(const GaussTmaParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int D = NB * 8;
   constexpr int kPitchU = D + 8;                 // doubles: conflict-free 128-bit reads of U rows
-  const int C = p.ncons, R = p.depth, S = C * R;
-  unsigned char* ring = smem_raw;
-  double* sU = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);   // D * kPitchU
-  double* sMu = sU + D * kPitchU;                                              // D
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sMu + D);
-  uint64_t* empty_bar = full_bar + kTmaMaxStages;
-  double* sRed = reinterpret_cast<double*>(empty_bar + kTmaMaxStages);
+  Ring ring;
+  ring.base = smem_raw;
+  ring.g = p.geom;
+  ring.d = D;
+  double* sU = reinterpret_cast<double*>(smem_raw + ring_bytes(p.geom));       // D * kPitchU
+  double* sMu = sU + D * kPitchU;                                               // D
+  ring.full_bar = reinterpret_cast<uint64_t*>(sMu + D);
+  ring.empty_bar = ring.full_bar + kRingMaxStages;
+  double* sRed = reinterpret_cast<double*>(ring.empty_bar + kRingMaxStages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < D * kPitchU; i += blockDim.x) {
     const int r = i / kPitchU, c = i - r * kPitchU;
     sU[i] = (c < D && c >= r) ? p.params[1 + D + size_t(r) * D + c] : 0.0;
   }
   for (int i = threadIdx.x; i < D; i += blockDim.x) sMu[i] = p.params[1 + i];
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  ring_init(ring);
   const double cst = p.params[0];
-  const int64_t ntiles = (p.n + kTmaRows - 1) / kTmaRows;
-  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t tile_bytes = uint32_t(kTmaRows) * uint32_t(D) * 8u;
+  const int64_t my_tiles = ring_my_tiles(p.n);
   double s_wl = 0.0, s_w = 0.0;
 
-  if (warp == kTmaConsumers) {
-    if (lane < C) {
-      int64_t r = 0;
-      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
-        const int stage = lane * R + int(r % R);
-        const uint32_t phase = uint32_t(r / R) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-        double* sW = reinterpret_cast<double*>(sX + tile_bytes);
-        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kTmaRows;
-        if (row0 + kTmaRows <= p.n) {
-          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + (p.w ? 256u : 0u));
-          bulk_g2s(sX, p.X + row0 * D, tile_bytes, &full_bar[stage]);
-          if (p.w) bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
-        } else {
-          const int rows = int(p.n - row0);
-          for (int i = 0; i < rows; ++i) sW[i] = p.w ? p.w[row0 + i] : 0.0;
-          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(D) * 8u);
-          bulk_g2s(sX, p.X + row0 * D, uint32_t(rows) * uint32_t(D) * 8u, &full_bar[stage]);
-        }
-      }
-    }
-  } else if (warp < C) {
+  if (warp == kRingConsumers) {
+    ring_produce(ring, p.X, nullptr, p.w, p.n, my_tiles, false);
+  } else if (warp < p.geom.ncons) {
     const int g = lane >> 2, t = lane & 3;
-    for (int64_t tl = warp; tl < my_tiles; tl += C) {
-      const int64_t r = tl / C;
-      const int stage = warp * R + int(r % R);
-      const uint32_t phase = uint32_t(r / R) & 1u;
-      mbar_wait(&full_bar[stage], phase);
-      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-      const double* sW = reinterpret_cast<const double*>(sX + tile_bytes);
+    for (int64_t tl = warp; tl < my_tiles; tl += p.geom.ncons) {
+      const RingStage st = ring_acquire(ring, warp, tl);
       double myquad = 0.0;
 #pragma unroll 1
       for (int grp = 0; grp < 4; ++grp) {
         // centred fragment of row 8 grp + g: features (8 kk + 2 t, + 1)
-        const double2* xrow = reinterpret_cast<const double2*>(sX + size_t(8 * grp + g) * D * 8);
+        const double2* xrow = reinterpret_cast<const double2*>(st.x + size_t(8 * grp + g) * D * 8);
         double2 c[NB];
 #pragma unroll
         for (int kk = 0; kk < NB; ++kk) {
@@ -580,10 +491,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) gaussian_tma_kernel(const Gaus
         const double got = __shfl_sync(0xffffffffu, quad, 4 * (lane & 7));
         if ((lane >> 3) == grp) myquad = got;
       }
-      const double wi = sW[lane];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      const int64_t row = (blockIdx.x + tl * gridDim.x) * kTmaRows + lane;
+      const double wi = st.w[lane];
+      ring_release(ring, st);
+      const int64_t row = ring_row0(tl) + lane;
       if (row < p.n) {
         const double loss = 0.5 * (myquad + cst);                    // utils.py:101
         if (p.losses) p.losses[row] = loss;
@@ -662,7 +572,7 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
       return RLVI_ERR_UNSUPPORTED;
     }
     // ---- TMA-fed path: d in {16, 32, 48, 64}, aligned, at least one full tile ------------------------
-    if (d % 16 == 0 && d <= 64 && n >= kTmaRows && rlvi_aligned16(X) && (!weights || rlvi_aligned16(weights))) {
+    if (d % 16 == 0 && d <= 64 && n >= kRingRows && rlvi_aligned16(X) && (!weights || rlvi_aligned16(weights))) {
       GaussTmaParams q;
       q.X = X;
       q.params = params;
@@ -672,24 +582,18 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
       q.wsum_out = wsum_out;
       q.n = n;
       q.d = d;
-      q.stage_bytes = kTmaRows * d * 8 + 256;
-      const size_t tail = (size_t(d) * (d + 8) + d) * 8 + 2 * kTmaMaxStages * 8 + 2 * (kTmaConsumers + 1) * 8 + 128;
-      const int max_stages = int((size_t(220) * 1024 - tail) / q.stage_bytes);
-      q.ncons = max_stages < kTmaConsumers ? max_stages : kTmaConsumers;
-      q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
-      if (q.depth > 2) q.depth = 2;
-      const int64_t ntiles = (n + kTmaRows - 1) / kTmaRows;
-      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
-      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+      const size_t tail = gauss_tma_tail(d);
+      if (!ring_geometry(d, tail, &q.geom)) return RLVI_ERR_UNSUPPORTED;
+      const int grid = ring_grid(q.geom, n, ctx->sm_count);
       int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * 2 * sizeof(double), &scratch);
       if (rc != RLVI_OK) return rc;
       q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
       q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-      const size_t smem = size_t(q.ncons) * q.depth * q.stage_bytes + tail;
+      const size_t smem = ring_bytes(q.geom) + tail;
 #define RLVI_GTMA_CASE(NB)                                                                                    \
   if (d == 8 * NB) {                                                                                          \
     RLVI_CUDA(cudaFuncSetAttribute(gaussian_tma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-    gaussian_tma_kernel<NB><<<grid, kTmaThreads, smem, st>>>(q);                                              \
+    gaussian_tma_kernel<NB><<<grid, kRingThreads, smem, st>>>(q);                                              \
     RLVI_LAUNCH_CHECK(ctx);                                                                                   \
     return RLVI_OK;                                                                                           \
   }
@@ -735,7 +639,7 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
   }
 
   // ---- TMA-fed path: d % 16 == 0, <= 256, all streamed arrays 16-byte aligned, at least one full tile ----
-  if (d % 16 == 0 && d <= 256 && n >= kTmaRows && rlvi_aligned16(X) && (!y || rlvi_aligned16(y)) &&
+  if (d % 16 == 0 && d <= 256 && n >= kRingRows && rlvi_aligned16(X) && (!y || rlvi_aligned16(y)) &&
       (!weights || rlvi_aligned16(weights))) {
     LossTmaParams q;
     q.X = X;
@@ -749,27 +653,18 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
     q.d = d;
     q.kind = kind;
     q.intercept = intercept ? 1 : 0;
-    q.stage_bytes = kTmaRows * d * 8 + 512;
-    const size_t tail = size_t(((d + 1) & ~1) + 2) * 8 + 2 * kTmaMaxStages * 8 + 2 * (kTmaConsumers + 1) * 8 + 128;
-    const int max_stages = int((size_t(220) * 1024 - tail) / q.stage_bytes);
-    q.ncons = max_stages < kTmaConsumers ? max_stages : kTmaConsumers;
-    q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
-    if (q.depth > 2) q.depth = 2;
-    const int stages = q.ncons * q.depth;
-    const int64_t ntiles = (n + kTmaRows - 1) / kTmaRows;
-    if (stages >= 2) {
-      q.nstages = stages;
-      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
-      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+    const size_t tail = loss_tma_tail(d);
+    if (ring_geometry(d, tail, &q.geom)) {
+      const int grid = ring_grid(q.geom, n, ctx->sm_count);
       int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * 2 * sizeof(double), &scratch);
       if (rc != RLVI_OK) return rc;
       q.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
       q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-      const size_t smem = size_t(stages) * q.stage_bytes + tail;
+      const size_t smem = ring_bytes(q.geom) + tail;
 #define RLVI_TMA_CASE(K)                                                                                   \
   {                                                                                                        \
     RLVI_CUDA(cudaFuncSetAttribute(loss_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-    loss_tma_kernel<K><<<grid, kTmaThreads, smem, st>>>(q);                                                \
+    loss_tma_kernel<K><<<grid, kRingThreads, smem, st>>>(q);                                                \
     RLVI_LAUNCH_CHECK(ctx);                                                                                \
     return RLVI_OK;                                                                                        \
   }

@@ -26,7 +26,7 @@
 #include <math.h>
 
 #include "rowmap.cuh"
-#include "tma.cuh"
+#include "tma_ring.cuh"
 
 namespace {
 
@@ -546,8 +546,8 @@ int launch_colsum(rlvi_ctx* ctx, const RowMapCfg& cfg, ColParams& p, int grid, s
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-fed column sums (d % 16 == 0, d <= 256, 16-byte aligned pointers): same skeleton as loss_tma_kernel
-// (loss.cu) -- one producer lane per consumer warp, private rings, ONE bulk copy per 32-row tile.
+// TMA-fed column sums (d % 16 == 0, d <= 256, 16-byte aligned pointers): the producer / private-ring skeleton
+// of tma_ring.cuh (shared with loss_tma_kernel) feeding a two-phase consumer.
 //   phase 1 (MODE 1 only): lane = row, rotated conflict-free walk, phi = b + x.theta,
 //                          c1 = w (sigmoid(phi) - y)                       utils.py:40-41
 //           (MODE 0)      : c1 = w, c2 = we * y                           rlvi.py:48,56,71,80
@@ -555,11 +555,6 @@ int launch_colsum(rlvi_ctx* ctx, const RowMapCfg& cfg, ColParams& p, int grid, s
 //            shared memory; every 128-bit read of x is one conflict-free wavefront per 8 lanes.
 // Per-warp d-vectors are summed in warp order, per-CTA partials in CTA order (sum_parts_kernel).
 // ---------------------------------------------------------------------------------------------
-constexpr int kCtConsumers = 16;
-constexpr int kCtThreads = (kCtConsumers + 1) * 32;
-constexpr int kCtRows = 32;
-constexpr int kCtMaxStages = 2 * kCtConsumers;
-
 struct ColTmaParams {
   const double* X;
   const double* y;
@@ -569,70 +564,40 @@ struct ColTmaParams {
   int64_t n;
   int d;
   int power;
-  int stage_bytes;   // kCtRows * d * 8 + 512 (y, w)
-  int ncons, depth;
+  RingGeom geom;
   double* partials;  // [grid][2 + 2 d]
 };
 
+static inline size_t colsum_tma_tail(int d) {
+  return size_t(d + 2) * 8 + kRingBarrierBytes + size_t(kRingConsumers) * 64 * 8 + size_t(kRingConsumers) * (2 + 2 * d) * 8 + 128;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaParams p) {
+__global__ void __launch_bounds__(kRingThreads, 1) colsum_tma_kernel(const ColTmaParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int C = p.ncons, R = p.depth, S = C * R;
-  unsigned char* ring = smem_raw;
-  double* sTheta = reinterpret_cast<double*>(ring + size_t(S) * p.stage_bytes);          // d (+ 2)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sTheta + p.d + 2);
-  uint64_t* empty_bar = full_bar + kCtMaxStages;
-  double* sC = reinterpret_cast<double*>(empty_bar + kCtMaxStages);                      // [C][2][32] row coefficients
-  double* sOut = sC + kCtConsumers * 64;                                                  // [C][2 + 2 d]
+  const int C = p.geom.ncons;
+  Ring ring;
+  ring.base = smem_raw;
+  ring.g = p.geom;
+  ring.d = p.d;
+  double* sTheta = reinterpret_cast<double*>(smem_raw + ring_bytes(p.geom));              // d (+ 2)
+  ring.full_bar = reinterpret_cast<uint64_t*>(sTheta + p.d + 2);
+  ring.empty_bar = ring.full_bar + kRingMaxStages;
+  double* sC = reinterpret_cast<double*>(ring.empty_bar + kRingMaxStages);                 // [C][2][32] row coefficients
+  double* sOut = sC + kRingConsumers * 64;                                                  // [C][2 + 2 d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = p.d, npair = d >> 1;
   const int stride = 2 + 2 * d;
   if (MODE == 1)
     for (int i = threadIdx.x; i < d; i += blockDim.x) sTheta[i] = p.params[1 + i];
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  ring_init(ring);
   const double b0 = (MODE == 1) ? p.params[0] : 0.0;
-  const int64_t ntiles = (p.n + kCtRows - 1) / kCtRows;
-  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t tile_bytes = uint32_t(kCtRows) * uint32_t(d) * 8u;
+  const int64_t my_tiles = ring_my_tiles(p.n);
   const bool has_y = p.y != nullptr;
 
-  if (warp == kCtConsumers) {
-    if (lane < C) {
-      int64_t r = 0;
-      for (int64_t t = lane; t < my_tiles; t += C, ++r) {
-        const int stage = lane * R + int(r % R);
-        const uint32_t phase = uint32_t(r / R) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-        double* sY = reinterpret_cast<double*>(sX + tile_bytes);
-        double* sW = sY + kCtRows;
-        const int64_t row0 = (blockIdx.x + t * gridDim.x) * kCtRows;
-        if (row0 + kCtRows <= p.n) {
-          mbar_arrive_expect_tx(&full_bar[stage], tile_bytes + 256u + (has_y ? 256u : 0u));
-          bulk_g2s(sX, p.X + row0 * d, tile_bytes, &full_bar[stage]);
-          if (has_y) bulk_g2s(sY, p.y + row0, 256, &full_bar[stage]);
-          bulk_g2s(sW, p.w + row0, 256, &full_bar[stage]);
-        } else {
-          const int rows = int(p.n - row0);
-          for (int i = 0; i < kCtRows; ++i) {       // rows past n: w = 0 -> no contribution (x there is stale but finite)
-            sY[i] = (has_y && i < rows) ? p.y[row0 + i] : 0.0;
-            sW[i] = (i < rows) ? p.w[row0 + i] : 0.0;
-          }
-          // stale rows could hold NaN bit patterns from an earlier tile of another call: clear them
-          double* sXd = reinterpret_cast<double*>(sX);
-          for (int i = rows * d; i < kCtRows * d; ++i) sXd[i] = 0.0;
-          mbar_arrive_expect_tx(&full_bar[stage], uint32_t(rows) * uint32_t(d) * 8u);
-          bulk_g2s(sX, p.X + row0 * d, uint32_t(rows) * uint32_t(d) * 8u, &full_bar[stage]);
-        }
-      }
-    }
+  if (warp == kRingConsumers) {
+    // rows past n of the ragged tile enter the sums with weight 0: clear them (a stale NaN x 0 would poison)
+    ring_produce(ring, p.X, p.y, p.w, p.n, my_tiles, true);
   } else if (warp < C) {
     const double2* th2 = reinterpret_cast<const double2*>(sTheta);
     double* myC = sC + warp * 64;
@@ -653,17 +618,11 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
     }
     double s0 = 0.0, swy = 0.0;
     for (int64_t t = warp; t < my_tiles; t += C) {
-      const int64_t r = t / C;
-      const int stage = warp * R + int(r % R);
-      const uint32_t phase = uint32_t(r / R) & 1u;
-      mbar_wait(&full_bar[stage], phase);
-      const unsigned char* sX = ring + size_t(stage) * p.stage_bytes;
-      const double* sY = reinterpret_cast<const double*>(sX + tile_bytes);
-      const double* sW = sY + kCtRows;
-      const double2* xt = reinterpret_cast<const double2*>(sX);
+      const RingStage st = ring_acquire(ring, warp, t);
+      const double2* xt = reinterpret_cast<const double2*>(st.x);
       // ---- phase 1: one row per lane -> its coefficients
-      const double w1 = sW[lane];
-      const double yi = has_y ? sY[lane] : 0.0;
+      const double w1 = st.w[lane];
+      const double yi = has_y ? st.y[lane] : 0.0;
       double c1, c2 = 0.0;
       if (MODE == 0) {
         const double we = (p.power == 2) ? w1 * w1 : w1;
@@ -699,7 +658,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
       __syncwarp();
       // ---- phase 2: lane = feature pair(s); acc += c_r * x[r][.] over the tile's rows
 #pragma unroll 4
-      for (int rr = 0; rr < kCtRows; ++rr) {
+      for (int rr = 0; rr < kRingRows; ++rr) {
         const double k1 = myC[rr];
         const double k2 = (MODE == 0) ? myC[32 + rr] : 0.0;
         const double2* xrow = xt + size_t(rr) * npair;
@@ -721,8 +680,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) colsum_tma_kernel(const ColTmaP
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      ring_release(ring, st);
     }
     // per-warp vector to shared memory
     double* mine = sOut + size_t(warp) * stride;
@@ -757,7 +715,7 @@ template <int MODE>
 int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w, const double* params,
                const double* center, int64_t n, int d, int power, double* out, int count, cudaStream_t st) {
   // ---- TMA-fed path -------------------------------------------------------------------------------
-  if (d % 16 == 0 && d <= 256 && n >= kCtRows && rlvi_aligned16(X) && rlvi_aligned16(w) && (!y || rlvi_aligned16(y))) {
+  if (d % 16 == 0 && d <= 256 && n >= kRingRows && rlvi_aligned16(X) && rlvi_aligned16(w) && (!y || rlvi_aligned16(y))) {
     ColTmaParams q;
     q.X = X;
     q.y = y;
@@ -767,25 +725,17 @@ int run_colsum(rlvi_ctx* ctx, const double* X, const double* y, const double* w,
     q.n = n;
     q.d = d;
     q.power = power;
-    q.stage_bytes = kCtRows * d * 8 + 512;
     const int stride = 2 + 2 * d;
-    const size_t tail = size_t(d + 2) * 8 + 2 * kCtMaxStages * 8 + size_t(kCtConsumers) * 64 * 8 +
-                        size_t(kCtConsumers) * stride * 8 + 128;
-    const int max_stages = int((size_t(224) * 1024 - tail) / q.stage_bytes);
-    q.ncons = max_stages < kCtConsumers ? max_stages : kCtConsumers;
-    q.depth = q.ncons > 0 ? max_stages / q.ncons : 0;
-    if (q.depth > 2) q.depth = 2;
-    if (q.ncons >= 2) {
-      const int64_t ntiles = (n + kCtRows - 1) / kCtRows;
-      const int64_t want_ctas = (ntiles + q.ncons - 1) / q.ncons;
-      const int grid = int(want_ctas < ctx->sm_count ? want_ctas : ctx->sm_count);
+    const size_t tail = colsum_tma_tail(d);
+    if (ring_geometry(d, tail, &q.geom)) {
+      const int grid = ring_grid(q.geom, n, ctx->sm_count);
       void* scratch = nullptr;
       int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * stride * sizeof(double), &scratch);
       if (rc != RLVI_OK) return rc;
       q.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-      const size_t smem = size_t(q.ncons) * q.depth * q.stage_bytes + tail;
+      const size_t smem = ring_bytes(q.geom) + tail;
       RLVI_CUDA(cudaFuncSetAttribute(colsum_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      colsum_tma_kernel<MODE><<<grid, kCtThreads, smem, st>>>(q);
+      colsum_tma_kernel<MODE><<<grid, kRingThreads, smem, st>>>(q);
       RLVI_LAUNCH_CHECK(ctx);
       sum_parts_kernel<<<(count + 255) / 256, 256, 0, st>>>(q.partials, grid, stride, count, MODE == 1 ? 1 : 0, out);
       RLVI_LAUNCH_CHECK(ctx);
