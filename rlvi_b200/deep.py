@@ -16,7 +16,8 @@ import torch
 
 from . import ops
 
-__all__ = ["train_rlvi", "update_sample_weights", "false_negative_criterion", "weighted_cross_entropy"]
+__all__ = ["train_rlvi", "update_sample_weights", "false_negative_criterion", "weighted_cross_entropy",
+           "selection_mask"]
 
 
 @torch.no_grad()
@@ -30,6 +31,12 @@ def update_sample_weights(residuals, weights, tol=1e-3, maxiter=40):
 def false_negative_criterion(weights, alpha=0.05):
     """train_rlvi.py:41-49 -- returns a 0-dim tensor on the weights' device."""
     return ops.fn_threshold(weights, alpha=alpha, prev_threshold=0.0, truncate=False).reshape(())
+
+
+@torch.no_grad()
+def selection_mask(weights, threshold):
+    """deep-learning/main.py:342 -- the samples the method currently treats as clean: weights > threshold."""
+    return weights > threshold
 
 
 class _WeightedCE(torch.autograd.Function):
