@@ -274,6 +274,32 @@ def run_b200(args):
             "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")},
             "host": {"cpus": os.cpu_count(), "inter_step_gap_ms": float(np.mean(gaps)) if gaps else 0.0}}
 
+    # ---- comparable-across-runs variant: exactly 32 fixed-point passes ---------------
+    def step_k32():
+        ops.loss(ops.LOSS_LOGISTIC_CE, X, params, y=y, intercept=True, want_losses=False, want_e=True, e_out=e)
+        ops.fixed_point(None, e_work=e, out=pi, result=res, tol=-1.0, maxiter=32,
+                        dist=group.fp_dist(n_total) if group else None)
+        ops.weighted_moments(X, pi, out=mom)
+        if group:
+            group.all_reduce(mom)
+
+    step_k32()
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        torch.distributed.all_reduce(torch.zeros(1, device=dev))
+    k0.record()
+    for _ in range(5):
+        step_k32()
+    k1.record()
+    barrier()
+    k32_ms = k0.elapsed_time(k1) / 5
+    if world > 1:
+        t = torch.tensor([k32_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        k32_ms = float(t)
+    line["fixed_k32"] = {"fixed_point_passes": 32, "ms_per_step": k32_ms, "value": n_total / (k32_ms * 1e-3), "steps": 5}
+
     # ---- e2e: the same step through the host-buffer C-ABI call, H2D/D2H inside the timed region --------
     if not args.no_e2e:
         line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total, group)
