@@ -2,7 +2,7 @@
 
     sigmoid(x)                                      utils.py:7-16
     cross_entropy(X, theta, y)                      utils.py:19-21
-    clf_predict(X, theta)                           utils.py:24-29
+    clf_predict(X, theta, augment=True)             utils.py:24-29
     mm_log_reg(X, y, weights)                       utils.py:32-58
     sklearn_log_reg(X, y, weights, reg_coeff=1e2)   utils.py:61-73
     pca(samples, weights, theta=None)               utils.py:76-89
@@ -49,13 +49,14 @@ def cross_entropy(X, theta, y):
     return to_caller(losses, was_np)
 
 
-def clf_predict(X, theta):
-    """utils.py:24-29 -- 0/1 predictions of [1, X] theta (sign of the linear predictor)."""
+def clf_predict(X, theta, augment=True):
+    """utils.py:24-29 -- 0/1 predictions (int): sigmoid([1, X] theta) > 0.5, or sigmoid(X theta) > 0.5 with
+    `augment=False`."""
     Xd, was_np = as_device(X)
     td, _ = as_device(theta, like=Xd)
     # softplus(phi) > log 2  <=>  phi > 0  <=>  sigmoid(phi) > 0.5
-    sp, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, td, intercept=True)
-    pred = (sp > math.log(2.0)).to(torch.float64)
+    sp, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, td, intercept=bool(augment))
+    pred = (sp > math.log(2.0)).to(torch.int64)
     return to_caller(pred, was_np)
 
 

@@ -160,6 +160,7 @@ def test_standard_signatures():
     assert sig(rlvi.covariance) == [("sample", E_), ("eps", E_), ("maxiter", 100), ("tol", 1e-2)]
     assert sig(utils.sigmoid) == [("x", E_)]
     assert sig(utils.cross_entropy) == [("X", E_), ("theta", E_), ("y", E_)]
+    assert sig(utils.clf_predict) == [("X", E_), ("theta", E_), ("augment", True)]
     assert sig(utils.mm_log_reg) == [("X", E_), ("y", E_), ("weights", E_)]
     assert sig(utils.sklearn_log_reg)[:4] == [("X", E_), ("y", E_), ("weights", E_), ("reg_coeff", 1e2)]
     assert sig(utils.pca) == [("samples", E_), ("weights", E_), ("theta", None)]
@@ -174,6 +175,41 @@ def test_deep_and_online_signatures():
                                                     "overfit", "threshold"]
     assert sig(online.update_weights_rlvi)[:3] == [("losses", E_), ("tol", 1e-3), ("maxiter", 100)]
     assert sig(online.cross_entropy) == [("log_proba", E_), ("targets", E_)]
+
+
+def test_all_dropin_signatures_match_the_reference_when_present():
+    """Every public function of the four reference files on the path has a drop-in with the same leading
+    argument names and the same defaults (extra keyword-only options are allowed after them)."""
+    import importlib
+    table = {"standard-learning/rlvi.py": "rlvi_b200.rlvi", "standard-learning/utils.py": "rlvi_b200.utils",
+             "deep-learning/methods/train_rlvi.py": "rlvi_b200.deep"}
+    if not os.path.exists("/root/reference/standard-learning/rlvi.py"):
+        pytest.skip("reference tree not present (GPU box)")
+    checked = 0
+    for rel, modname in table.items():
+        mod = importlib.import_module(modname)
+        tree = ast.parse(open(os.path.join("/root/reference", rel)).read())
+        for node in tree.body:
+            if not isinstance(node, ast.FunctionDef):
+                continue
+            ours = getattr(mod, node.name)
+            ref_args = [a.arg for a in node.args.args]
+            ref_defaults = [ast.literal_eval(dflt) for dflt in node.args.defaults]
+            mine = sig(ours)[:len(ref_args)]
+            assert [n for n, _ in mine] == ref_args, (rel, node.name)
+            if ref_defaults:
+                assert [dv for _, dv in mine[-len(ref_defaults):]] == ref_defaults, (rel, node.name)
+            checked += 1
+    # online-learning/main.py: only the two RLVI functions are on the path
+    from rlvi_b200 import online
+    tree = ast.parse(open("/root/reference/online-learning/main.py").read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("update_weights_rlvi", "cross_entropy"):
+            ours = getattr(online, node.name)
+            ref_args = [a.arg for a in node.args.args]
+            assert [n for n, _ in sig(ours)][:len(ref_args)] == ref_args
+            checked += 1
+    assert checked >= 18
 
 
 def test_signatures_match_the_reference_when_present():

@@ -532,6 +532,19 @@ def test_mm_log_reg_and_logistic_regression_golden(dev):
     assert relmax(rlvi.logistic_regression(g2["X"], g2["y"], mstep="mm"), g2["theta"]) < 1e-8
 
 
+def test_clf_predict(dev):
+    from rlvi_b200 import utils
+    rng = np.random.default_rng(12)
+    X = rng.normal(size=(500, 7))
+    theta = rng.normal(size=8)
+    Xa = np.hstack([np.ones((500, 1)), X])
+    ref = np.array(rlvi_np.sigmoid(Xa @ theta) > 0.5, dtype=int)          # utils.py:24-29
+    out = utils.clf_predict(X, theta)
+    assert out.dtype.kind == "i" and np.array_equal(out, ref)
+    ref2 = np.array(rlvi_np.sigmoid(X @ theta[1:]) > 0.5, dtype=int)
+    assert np.array_equal(utils.clf_predict(X, theta[1:], augment=False), ref2)
+
+
 def test_sklearn_log_reg_golden(dev):
     """liblinear is third-party and stops at tol = 1e-4: agreement is to liblinear's accuracy; the
     in-place normalisation of the caller's weights (Q3) and the label-independent loss are exact."""
