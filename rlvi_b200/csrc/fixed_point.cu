@@ -314,9 +314,21 @@ __device__ __forceinline__ double2 ld_e2(const double2* p) {
 // shard is 64 MiB and ~40 % of it fits the 148 x ~216 KB of shared memory, which cuts the L2 traffic of the
 // L2-bound passes by that much; the values are identical to the global ones, so results do not change.
 struct ECache {
-  double2* buf;    // [slots][blockDim.x]
-  int slots;
+  double2* buf;    // cache: [slots][blockDim.x]; ring: [kFpRingDepth][kFpUnroll][blockDim.x]
+  int slots;       // > 0: the first `slots` chunks of every thread are resident (small shards)
+  int ring;        // != 0: the buffer is a per-thread cp.async prefetch ring instead (HBM-sized vectors)
 };
+constexpr int kFpRingDepth = 3;   // trips in flight per thread: 3 x 8 x 16 B = 384 B (registers hold only the current trip)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ double2 ld_e2c(const ECache& ec, int slot, const double2* gptr) {
   return (slot < ec.slots) ? ec.buf[slot * kFpThreads + threadIdx.x] : ld_e2(gptr);
 }
@@ -354,6 +366,69 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, const ECache& e
   int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
   int slot0 = 0;
+  if (ec.ring) {
+    // HBM-sized vector: every thread keeps kFpRingDepth trips in flight with cp.async (LDGSTS) into its own
+    // slots of the ring -- 384 B per thread outstanding instead of the 128 B the registers can hold -- and
+    // computes on the oldest trip.  Same grid-stride chunk ownership as every other pass, and a thread only
+    // reads what it copied itself: no barrier needed.  (Measured 2.94 -> 2.87 ms at 2^26; a blocked,
+    // CTA-contiguous mapping was no better: the pass is not limited by memory-level parallelism any more.)
+    const int64_t ntrips =
+        (nvec > c + (kFpUnroll - 1) * stride) ? (nvec - c - (kFpUnroll - 1) * stride - 1) / (kFpUnroll * stride) + 1 : 0;
+    double2* ring = ec.buf + threadIdx.x;
+    auto issue = [&](int64_t j, int slot) {
+      const double2* src = ev + c + j * kFpUnroll * stride;
+#pragma unroll
+      for (int u = 0; u < kFpUnroll; ++u) cp_async16(ring + (slot * kFpUnroll + u) * kFpThreads, src + u * stride);
+    };
+#pragma unroll
+    for (int j = 0; j < kFpRingDepth - 1; ++j) {
+      if (j < ntrips) issue(j, j);
+      cp_async_commit();
+    }
+    int rd = 0, wr = kFpRingDepth - 1;
+    for (int64_t j = 0; j < ntrips; ++j) {
+      if (j + kFpRingDepth - 1 < ntrips) issue(j + kFpRingDepth - 1, wr);
+      cp_async_commit();                       // one group per iteration keeps the wait count uniform
+      cp_async_wait<kFpRingDepth - 1>();       // trip j has landed
+      double2 v[kFpUnroll];
+#pragma unroll
+      for (int u = 0; u < kFpUnroll; ++u) v[u] = ring[(rd * kFpUnroll + u) * kFpThreads];
+      double t1a = 0.0, t1b = 0.0, t2a = 0.0, t2b = 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int u = 0; u < kFpUnroll; ++u) {
+        double pn, d;
+        post_pair_fast<VARIANT>(v[u].x, rho_new, rho_old, drho, pn, d, ok);
+        t1a += pn;
+        t2a = fma(d, d, t2a);
+        post_pair_fast<VARIANT>(v[u].y, rho_new, rho_old, drho, pn, d, ok);
+        t1b += pn;
+        t2b = fma(d, d, t2b);
+      }
+      if (!ok) {
+        t1a = t1b = t2a = t2b = 0.0;
+#pragma unroll 1
+        for (int u = 0; u < kFpUnroll; ++u) {
+          const double2 w = ld_e2(ev + c + (j * kFpUnroll + u) * stride);
+          double pn, d;
+          post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
+          t1a += pn;
+          t2a = fma(d, d, t2a);
+          post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
+          t1b += pn;
+          t2b = fma(d, d, t2b);
+        }
+      }
+      s1a += t1a;
+      s1b += t1b;
+      s2a += t2a;
+      s2b += t2b;
+      rd = (rd + 1 == kFpRingDepth) ? 0 : rd + 1;
+      wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
+    }
+    cp_async_wait<0>();
+    c += ntrips * kFpUnroll * stride;          // the remainder trip below takes it from here
+  }
   for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
     double2 v[kFpUnroll];
     if (slot0 + kFpUnroll <= ec.slots) {   // whole trip on chip (uniform branch; keeps the 8 loads back to back)
@@ -539,7 +614,8 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   extern __shared__ __align__(16) unsigned char fp_dyn_smem[];
   ECache ec;
   ec.buf = reinterpret_cast<double2*>(fp_dyn_smem);
-  ec.slots = VEC ? p.cache_slots : 0;
+  ec.slots = (VEC && p.cache_slots > 0) ? p.cache_slots : 0;
+  ec.ring = (VEC && p.cache_slots < 0) ? 1 : 0;      // cache_slots < 0 selects the prefetch ring
   const int64_t chunk0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t cstride = int64_t(gridDim.x) * blockDim.x;
 
@@ -968,7 +1044,7 @@ int launch_fp_small(rlvi_ctx* ctx, K kernel, const FpParams<T>& p, cudaStream_t 
 template <typename T, typename K>
 int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStream_t stream, int cache_slots = 0) {
   int per_sm = 0;
-  const size_t dyn_smem = size_t(cache_slots) * kFpThreads * sizeof(double2);
+  const size_t dyn_smem = size_t(cache_slots < 0 ? kFpRingDepth * kFpUnroll : cache_slots) * kFpThreads * sizeof(double2);
   p.cache_slots = cache_slots;
   if (dyn_smem > 0)
     RLVI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
@@ -1039,10 +1115,11 @@ static int fp_cache_slots(int64_t n) {
   static const char* env = getenv("RLVI_FP_CACHE_SLOTS");
   if (env) {
     const int v = atoi(env);
-    return v < 0 ? 0 : (v > kFpCacheSlots ? kFpCacheSlots : v);
+    return v < 0 ? -1 : (v > kFpCacheSlots ? kFpCacheSlots : v);
   }
-  (void)n;
-  return kFpCacheSlots;     // measured: 0.58 -> 0.50 ms at 2^23 samples, 3.13 -> 3.04 ms at 2^26
+  // <= 2^25 samples (16 trips per thread on a full grid): keep the head of the vector resident
+  // (measured 0.58 -> 0.50 ms at 2^23); larger: the buffer becomes a cp.async prefetch ring (-1)
+  return n <= (int64_t(1) << 25) ? kFpCacheSlots : -1;
 }
 
 extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
