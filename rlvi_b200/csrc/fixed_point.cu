@@ -20,7 +20,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -286,11 +286,6 @@ __device__ __forceinline__ double rcp_fast(double x) {
   t = fma(-x, r, 1.0);
   return fma(r, t, r);
 }
-// true if 2^-900 <= |x| < 2^900 (integer test on the exponent field: keeps the FP64 pipe free)
-__device__ __forceinline__ bool in_safe_range(double x) {
-  const unsigned int ex = (unsigned int)(__double2hiint(x) >> 20) & 0x7ffu;
-  return (ex - 123u) < 1800u;
-}
 
 // pi' and (pi' - pi) with the reference's own two IEEE divisions (scalar / unaligned path, loop tails and
 // the out-of-range fallback of the fast path below).
@@ -316,118 +311,142 @@ __device__ __forceinline__ double2 ld_e2(const double2* p) {
 struct ECache {
   double2* buf;    // cache: [slots][blockDim.x]; ring: [kFpRingDepth][kFpUnroll][blockDim.x]
   int slots;       // > 0: the first `slots` chunks of every thread are resident (small shards)
-  int ring;        // != 0: the buffer is a per-thread cp.async prefetch ring instead (HBM-sized vectors)
+  int ring;        // != 0: the buffer is a per-WARP TMA prefetch ring instead (HBM-sized vectors)
+  uint64_t* bars;  // ring mode: [warps][kFpRingDepth] mbarriers (kernel lifetime; phases persist across passes)
+  uint32_t phase;  // ring mode: bit s = parity to wait for on this warp's slot s
 };
-constexpr int kFpRingDepth = 3;   // trips in flight per thread: 3 x 8 x 16 B = 384 B (registers hold only the current trip)
+constexpr int kFpRingDepth = 3;   // 4 KiB slots per warp (8 warps x 3 x 4 KiB = 96 KiB per CTA)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ double2 ld_e2c(const ECache& ec, int slot, const double2* gptr) {
   return (slot < ec.slots) ? ec.buf[slot * kFpThreads + threadIdx.x] : ld_e2(gptr);
 }
 
-// Branch-free fast evaluation of (pi', pi' - pi); `ok` is cleared when the operand left the safe range,
-// in which case the caller redoes the whole trip with post_pair_f64's IEEE divisions.
+// Branch-free fast evaluation of one trip (kFpUnroll chunks of two samples).  The issue slots are what bounds
+// the hot pass (ncu: 27 warp-instructions per sample and pass, 11 of them FP64 at half issue rate), so:
+//   * no per-sample range test -- an operand outside rcp_fast's domain (rho = inf, e = inf or 0/0, a denormal
+//     product) surfaces as a NaN / inf in the trip's sums, which the caller tests ONCE per trip and then redoes
+//     the trip with the IEEE divisions;
+//   * STANDARD accumulates sum t^2 and the caller multiplies by (rho_old - rho_new)^2 once per pass
+//     (pi' - pi = t (rho_old - rho_new)): one DMUL per sample less.
+// q2 = sum t^2 (STANDARD) or sum (pi' - pi)^2 (ONLINE).
 template <int VARIANT>
-__device__ __forceinline__ void post_pair_fast(double e, double rho_new, double rho_old, double drho, double& pnew,
-                                               double& diff, bool& ok) {
-  if (VARIANT == RLVI_FP_STANDARD) {
-    const double a = rho_new + e, b = rho_old + e;
-    const double prod = a * b;
-    ok = ok && in_safe_range(prod);
-    const double t = e * rcp_fast(prod);
-    pnew = t * b;
-    diff = t * drho;                       // drho = rho_old - rho_new
-  } else {
-    const double a = rho_new * e, b = rho_old * e;
-    const double b1 = 1.0 + b;
-    const double prod = (1.0 + a) * b1;
-    ok = ok && in_safe_range(prod);
-    const double t = rcp_fast(prod);
-    pnew = a * b1 * t;
-    diff = (a - b) * t;
+__device__ __forceinline__ void trip_fast(const double2 (&v)[kFpUnroll], double rho_new, double rho_old, double& t1a,
+                                          double& t1b, double& q2a, double& q2b) {
+  auto one = [&](double e, double& t1, double& q2) {
+    if (VARIANT == RLVI_FP_STANDARD) {
+      const double b = rho_old + e;
+      const double t = e * rcp_fast((rho_new + e) * b);
+      t1 = fma(t, b, t1);                  // pi' = t (rho_old + e)
+      q2 = fma(t, t, q2);
+    } else {
+      const double a = rho_new * e, b = rho_old * e;
+      const double b1 = 1.0 + b;
+      const double t = rcp_fast((1.0 + a) * b1);
+      const double d = (a - b) * t;
+      t1 = fma(a * b1, t, t1);
+      q2 = fma(d, d, q2);
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < kFpUnroll; ++u) {
+    one(v[u].x, t1a, q2a);
+    one(v[u].y, t1b, q2b);
   }
+}
+__device__ __forceinline__ bool finite_f64(double x) {
+  return (((unsigned int)__double2hiint(x) >> 20) & 0x7ffu) != 0x7ffu;
 }
 
 template <int VARIANT>
-__device__ __forceinline__ void stream_pass_vec(const double* e, const ECache& ec, int64_t n, double rho_new,
+__device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int64_t n, double rho_new,
                                                 double rho_old, double& s1, double& s2) {
   const double2* ev = reinterpret_cast<const double2*>(e);
   const int64_t nvec = n >> 1;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   const double drho = rho_old - rho_new;
   int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+  double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;   // s2*: exact (pi' - pi)^2 sums of the IEEE-path samples
+  double q2sa = 0.0, q2sb = 0.0;                        // fast trips: sum t^2 (STANDARD) / sum d^2 (ONLINE)
   int slot0 = 0;
   if (ec.ring) {
-    // HBM-sized vector: every thread keeps kFpRingDepth trips in flight with cp.async (LDGSTS) into its own
-    // slots of the ring -- 384 B per thread outstanding instead of the 128 B the registers can hold -- and
-    // computes on the oldest trip.  Same grid-stride chunk ownership as every other pass, and a thread only
-    // reads what it copied itself: no barrier needed.  (Measured 2.94 -> 2.87 ms at 2^26; a blocked,
-    // CTA-contiguous mapping was no better: the pass is not limited by memory-level parallelism any more.)
-    const int64_t ntrips =
-        (nvec > c + (kFpUnroll - 1) * stride) ? (nvec - c - (kFpUnroll - 1) * stride - 1) / (kFpUnroll * stride) + 1 : 0;
-    double2* ring = ec.buf + threadIdx.x;
+    // HBM-sized vector: every WARP streams its own contiguous segment through a private ring of
+    // kFpRingDepth x 4 KiB slots filled by the TMA engine (one cp.async.bulk per 256-chunk trip, issued by
+    // lane 0, completing on the slot's mbarrier): 8-12 KiB per warp in flight without holding registers, and
+    // bulk requests reach ~6.6 TB/s where per-thread 16-byte loads (LDG or LDGSTS) level off at ~5.7 TB/s.
+    // e[] reached L2 before the previous grid barrier; the bulk copies read L2.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarpTrip = kFpUnroll * 32;                     // chunks per warp trip (4 KiB)
+    const int64_t nwarps = int64_t(gridDim.x) * (kFpThreads / 32);
+    const int64_t wg = int64_t(blockIdx.x) * (kFpThreads / 32) + warp;
+    const int64_t seg = (nvec + nwarps - 1) / nwarps;
+    const int64_t lo = wg * seg < nvec ? wg * seg : nvec;
+    const int64_t hi = (lo + seg < nvec) ? lo + seg : nvec;
+    const int64_t ntrips = (hi - lo) / kWarpTrip;
+    double2* ringw = ec.buf + size_t(warp) * kFpRingDepth * kWarpTrip;
+    uint64_t* bar = ec.bars + warp * kFpRingDepth;
+    uint32_t phase = ec.phase;
     auto issue = [&](int64_t j, int slot) {
-      const double2* src = ev + c + j * kFpUnroll * stride;
-#pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) cp_async16(ring + (slot * kFpUnroll + u) * kFpThreads, src + u * stride);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bar[slot], kWarpTrip * 16);
+        bulk_g2s(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, kWarpTrip * 16, &bar[slot]);
+      }
     };
 #pragma unroll
-    for (int j = 0; j < kFpRingDepth - 1; ++j) {
+    for (int j = 0; j < kFpRingDepth - 1; ++j)
       if (j < ntrips) issue(j, j);
-      cp_async_commit();
-    }
     int rd = 0, wr = kFpRingDepth - 1;
     for (int64_t j = 0; j < ntrips; ++j) {
-      if (j + kFpRingDepth - 1 < ntrips) issue(j + kFpRingDepth - 1, wr);
-      cp_async_commit();                       // one group per iteration keeps the wait count uniform
-      cp_async_wait<kFpRingDepth - 1>();       // trip j has landed
+      if (j + kFpRingDepth - 1 < ntrips) issue(j + kFpRingDepth - 1, wr);   // slot wr was read in iteration j - 1
+      mbar_wait(&bar[rd], (phase >> rd) & 1u);
+      phase ^= 1u << rd;
       double2 v[kFpUnroll];
 #pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) v[u] = ring[(rd * kFpUnroll + u) * kFpThreads];
-      double t1a = 0.0, t1b = 0.0, t2a = 0.0, t2b = 0.0;
-      bool ok = true;
-#pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) {
-        double pn, d;
-        post_pair_fast<VARIANT>(v[u].x, rho_new, rho_old, drho, pn, d, ok);
-        t1a += pn;
-        t2a = fma(d, d, t2a);
-        post_pair_fast<VARIANT>(v[u].y, rho_new, rho_old, drho, pn, d, ok);
-        t1b += pn;
-        t2b = fma(d, d, t2b);
-      }
-      if (!ok) {
-        t1a = t1b = t2a = t2b = 0.0;
+      for (int u = 0; u < kFpUnroll; ++u) v[u] = ringw[rd * kWarpTrip + u * 32 + lane];
+      __syncwarp();                              // every lane has its data: the slot may be re-armed next trip
+      double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
+      trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+      if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
+        s1a += t1a;
+        s1b += t1b;
+        q2sa += q2a;
+        q2sb += q2b;
+      } else {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
 #pragma unroll 1
         for (int u = 0; u < kFpUnroll; ++u) {
-          const double2 w = ld_e2(ev + c + (j * kFpUnroll + u) * stride);
+          const double2 w = ld_e2(ev + lo + j * kWarpTrip + u * 32 + lane);
           double pn, d;
           post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
-          t1a += pn;
-          t2a = fma(d, d, t2a);
+          s1a += pn;
+          s2a = fma(d, d, s2a);
           post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
-          t1b += pn;
-          t2b = fma(d, d, t2b);
+          s1b += pn;
+          s2b = fma(d, d, s2b);
         }
       }
-      s1a += t1a;
-      s1b += t1b;
-      s2a += t2a;
-      s2b += t2b;
       rd = (rd + 1 == kFpRingDepth) ? 0 : rd + 1;
       wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
     }
-    cp_async_wait<0>();
-    c += ntrips * kFpUnroll * stride;          // the remainder trip below takes it from here
+    ec.phase = phase;
+    // remainder of the warp's segment (< one trip): one predicated batch of direct loads
+    {
+      const int64_t r0 = lo + ntrips * kWarpTrip + lane;
+      double2 v[kFpUnroll];
+#pragma unroll
+      for (int u = 0; u < kFpUnroll; ++u) v[u] = (r0 + u * 32 < hi) ? ld_e2(ev + r0 + u * 32) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < kFpUnroll; ++u) {
+        if (r0 + u * 32 < hi) {
+          double pn, d;
+          post_pair_f64<VARIANT>(v[u].x, rho_new, rho_old, pn, d);
+          s1a += pn;
+          s2a = fma(d, d, s2a);
+          post_pair_f64<VARIANT>(v[u].y, rho_new, rho_old, pn, d);
+          s1b += pn;
+          s2b = fma(d, d, s2b);
+        }
+      }
+    }
+    c = nvec;                                    // the grid-stride loops below have nothing left to do
   }
   for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
     double2 v[kFpUnroll];
@@ -438,36 +457,26 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, const ECache& e
 #pragma unroll
       for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
     }
-    double t1a = 0.0, t1b = 0.0, t2a = 0.0, t2b = 0.0;
-    bool ok = true;
-#pragma unroll
-    for (int u = 0; u < kFpUnroll; ++u) {
-      double pn, d;
-      post_pair_fast<VARIANT>(v[u].x, rho_new, rho_old, drho, pn, d, ok);
-      t1a += pn;
-      t2a = fma(d, d, t2a);
-      post_pair_fast<VARIANT>(v[u].y, rho_new, rho_old, drho, pn, d, ok);
-      t1b += pn;
-      t2b = fma(d, d, t2b);
-    }
-    if (!ok) {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
-      t1a = t1b = t2a = t2b = 0.0;
+    double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
+    trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+    if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
+      s1a += t1a;
+      s1b += t1b;
+      q2sa += q2a;
+      q2sb += q2b;
+    } else {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
 #pragma unroll 1
       for (int u = 0; u < kFpUnroll; ++u) {
         const double2 w = ld_e2c(ec, slot0 + u, ev + c + u * stride);   // re-load: keeps v[] in registers
         double pn, d;
         post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
-        t1a += pn;
-        t2a = fma(d, d, t2a);
+        s1a += pn;
+        s2a = fma(d, d, s2a);
         post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
-        t1b += pn;
-        t2b = fma(d, d, t2b);
+        s1b += pn;
+        s2b = fma(d, d, s2b);
       }
     }
-    s1a += t1a;
-    s1b += t1b;
-    s2a += t2a;
-    s2b += t2b;
   }
   if (c < nvec) {
     // remainder: ONE predicated trip with all loads in flight together (a chunk-at-a-time tail loop costs a
@@ -498,7 +507,7 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, const ECache& e
     s2a = fma(d, d, s2a);
   }
   s1 = s1a + s1b;
-  s2 = s2a + s2b;
+  s2 = (s2a + s2b) + ((VARIANT == RLVI_FP_STANDARD) ? (drho * drho) * (q2sa + q2sb) : (q2sa + q2sb));
 }
 
 // Pass 1 over a precomputed, 16-byte aligned e[] (the loss kernel wrote it): pi' against the constant
@@ -616,6 +625,16 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   ec.buf = reinterpret_cast<double2*>(fp_dyn_smem);
   ec.slots = (VEC && p.cache_slots > 0) ? p.cache_slots : 0;
   ec.ring = (VEC && p.cache_slots < 0) ? 1 : 0;      // cache_slots < 0 selects the prefetch ring
+  __shared__ uint64_t fp_ring_bars[(kFpThreads / 32) * kFpRingDepth];
+  ec.bars = fp_ring_bars;
+  ec.phase = 0u;
+  if (ec.ring) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < (kFpThreads / 32) * kFpRingDepth; ++i) mbar_init(&fp_ring_bars[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   const int64_t chunk0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t cstride = int64_t(gridDim.x) * blockDim.x;
 
@@ -683,6 +702,9 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
       });
     }
     if (k == 1) {
+      // ring mode reads e[] with the TMA engine (async proxy) in the later passes: order this thread's generic
+      // stores of e before them (the grid barrier below then publishes them to the other CTAs)
+      if (ec.ring && have_losses) asm volatile("fence.proxy.async;" ::: "memory");
       ok = grid_allreduce3<double, OP_MAX>(p, sh, s1, s2, mx, round);
       emax = mx;
     } else {
