@@ -294,10 +294,9 @@ __global__ void __launch_bounds__(256) shift_sum_kernel(const double* __restrict
 __device__ __forceinline__ double shift_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double t = fma(-x, r, 1.0);
-  r = fma(r, t, r);
-  t = fma(-x, r, 1.0);
-  return fma(r, t, r);
+  const double d = fma(-x, r, 1.0);      // r (1 + d + d^2): see rcp_fast in fixed_point.cu
+  const double s = fma(d, d, d);
+  return fma(r, s, r);
 }
 __global__ void __launch_bounds__(256) shift_sum_e_kernel(const double* __restrict__ e, int64_t n, double scale_t,
                                                           double c, double* pi_out, double* partials,

@@ -275,16 +275,17 @@ __device__ __forceinline__ double post_f64(double e, double rho) {
   return a / (1.0 + a);
 }
 
-// 1/x for x in the normal range, to <= 1 ulp: MUFU.RCP64H seed (~2^-23) + two Newton steps (4 DFMA).
-// The IEEE division the compiler emits for `e / prod` costs ~25 instructions and a slow-path branch; the
-// fixed point evaluates it 2^26 x K times, which made the pass FP64-issue bound instead of HBM bound.
+// 1/x for x in the normal range to <= 1 ulp: MUFU.RCP64H seed r0 (relative error d ~ 2^-20), then ONE
+// second-order correction  r = r0 (1 + d + d^2)  -- 3 dependent DFMA, residual d^3 ~ 2^-60 -- instead of two
+// Newton steps (4 DFMA).  The IEEE division the compiler emits for `e / prod` is ~25 instructions with a slow
+// path; the hot pass is bound by FP64 issue (tools/ubench_fp.cu: realistic DFMA/DADD/DMUL mixes run at about half
+// the DFMA peak because of operand bandwidth), so every FP64 instruction per sample counts.
 __device__ __forceinline__ double rcp_fast(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double t = fma(-x, r, 1.0);
-  r = fma(r, t, r);
-  t = fma(-x, r, 1.0);
-  return fma(r, t, r);
+  const double d = fma(-x, r, 1.0);
+  const double s = fma(d, d, d);
+  return fma(r, s, r);
 }
 
 // pi' and (pi' - pi) with the reference's own two IEEE divisions (scalar / unaligned path, loop tails and
