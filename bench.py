@@ -167,6 +167,7 @@ def run_b200(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_cpus(local) if world > 1 else None
     group = rdist.ShardGroup.create(dev) if world > 1 else None
 
     n_total = 1 << args.log2n
@@ -272,7 +273,8 @@ def run_b200(args):
                            l2="inputs larger than L2 (X shard %.1f GiB streamed twice per step)" % (n * d * 8 / 2 ** 30)),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")},
-            "host": {"cpus": os.cpu_count(), "inter_step_gap_ms": float(np.mean(gaps)) if gaps else 0.0}}
+            "host": {"cpus": os.cpu_count(), "inter_step_gap_ms": float(np.mean(gaps)) if gaps else 0.0,
+                     "cpus_local_to_gpu": numa}}
 
     # ---- comparable-across-runs variant: exactly 32 fixed-point passes ---------------
     def step_k32():
@@ -313,6 +315,25 @@ def run_b200(args):
     if world > 1:
         group.close()
         torch.distributed.destroy_process_group()
+
+
+def pin_to_gpu_cpus(index):
+    """Multi-GPU runs: restrict this rank to the CPU cores NVML reports as local to its GPU, so that the pinned host
+    buffers of the e2e leg are allocated on the GPU's NUMA node (eight ranks copying from one socket's memory share
+    its bandwidth and the inter-socket link).  Returns the number of cores, or None when NVML does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def run_e2e(args, X, y, params, dev, world, rank, n_total, group):
