@@ -122,7 +122,7 @@ int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const
 
 /* Same, starting from the initial posterior `pi0` in (0, 1) instead of the variant's constant.  The reference
  * restarts every online batch from 0.5 (online-learning/main.py:48, quirk Q11); carrying the previous batch's
- * mean posterior (1 - result.eps) into the next call is the OPT-IN extension BASELINE.json's config 4 names. */
+ * mean posterior (result.sum_pi / n) into the next call is the OPT-IN extension BASELINE.json's config 4 names. */
 int rlvi_fixed_point_init_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
                               double* e_work, int64_t n, double tol, int maxiter, double pi0, double* pi_out,
                               rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
