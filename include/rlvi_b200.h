@@ -15,9 +15,12 @@
  *    `*_host` convenience calls, which say so;
  *  - scratch memory lives in the context (rlvi_ctx): it grows on demand (a cudaMalloc, the only place
  *    an allocation can happen) and is reused, so steady-state calls never allocate;
+ *  - because the scratch is shared, the calls made on ONE context must be stream-ordered with respect
+ *    to each other (one stream, or streams the caller chains with events); for concurrent streams or
+ *    host threads create one context per stream -- contexts are independent and cheap (8 MiB);
  *  - return value: 0 = RLVI_OK, < 0 = error; rlvi_last_error() gives the thread-local message;
- *  - reductions are deterministic (fixed-order two-stage trees, no floating-point atomics): the same
- *    inputs on the same GPU model give the same bits on every run.
+ *  - reductions are deterministic (fixed-order trees over warps, CTAs and ranks; no floating-point
+ *    atomics): the same inputs on the same GPU model and world size give the same bits on every run.
  */
 #ifndef RLVI_B200_H
 #define RLVI_B200_H
@@ -159,8 +162,10 @@ enum rlvi_loss_kind {
   RLVI_LOSS_SQDIST = 3,
   /* utils.py:77-79 PCA reconstruction: l = ||x||^2 - (x.theta)^2.   params = [theta(d)].          */
   RLVI_LOSS_PCA = 4,
-  /* utils.py:93-101 Gaussian NLL: l = 0.5 [(x-mu)^T P (x-mu) + c].
-   * params = [c, mu(d), P(d*d) row-major] with P = cov^-1, c = log|cov| + d log(2 pi).            */
+  /* utils.py:93-101 Gaussian NLL: l = 0.5 [(x-mu)^T cov^-1 (x-mu) + c] = 0.5 [||U (x-mu)||^2 + c].
+   * params = [c, mu(d), U(d*d) row-major], U UPPER triangular with U^T U = cov^-1 (the inverse of
+   * an upper Cholesky factor of cov; entries below the diagonal are ignored),
+   * c = log|cov| + d log(2 pi).  d <= 128.                                                        */
   RLVI_LOSS_GAUSSIAN = 5
 };
 

@@ -48,9 +48,14 @@ extern "C" int rlvi_ctx_create(int device, rlvi_ctx** out) {
     rlvi_set_error("cudaMallocHost failed");
     return RLVI_ERR_NOMEM;
   }
-  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
-  RLVI_CUDA(cudaDeviceSynchronize());
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    rlvi_set_error("context set-up -> %s", cudaGetErrorString(e));
+    rlvi_ctx_destroy(ctx);
+    return RLVI_ERR_CUDA;
+  }
   *out = ctx;
   return RLVI_OK;
 }
@@ -85,7 +90,11 @@ int rlvi_scratch(rlvi_ctx* ctx, size_t bytes, void** out) {
       rlvi_set_error("cudaMalloc of %zu scratch bytes failed", want);
       return RLVI_ERR_NOMEM;
     }
-    RLVI_CUDA(cudaMemset(p, 0, want));
+    if (cudaMemset(p, 0, want) != cudaSuccess) {
+      cudaFree(p);
+      rlvi_set_error("cudaMemset of the new scratch failed");
+      return RLVI_ERR_CUDA;
+    }
     cudaFree(ctx->scratch);
     ctx->scratch = p;
     ctx->scratch_bytes = want;

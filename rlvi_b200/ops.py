@@ -40,6 +40,19 @@ def _chk(t, dtype, name):
     return t
 
 
+def _len(t, n, name):
+    """The C side sees raw pointers only: every length is checked here."""
+    if t is not None and t.numel() != n:
+        raise ValueError(f"{name} must have {n} elements (got {t.numel()})")
+    return t
+
+
+def _same_device(ref, *tensors):
+    for t in tensors:
+        if t is not None and t.device != ref.device:
+            raise ValueError(f"all tensors of one call must live on {ref.device} (got {t.device})")
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -78,8 +91,16 @@ def fixed_point(losses=None, *, e_work=None, scale=None, variant=FP_STANDARD, to
         out = torch.empty(n, dtype=f64, device=ref.device)
     _chk(out, f64, "out")
     _chk(scale, f64, "scale")
+    if n == 0:
+        raise ValueError("empty loss vector")
+    _len(e_work, n, "e_work")
+    _len(out, n, "out")
+    _len(scale, 1, "scale")
     if result is None:
         result = torch.empty(5, dtype=f64, device=ref.device)
+    _chk(result, f64, "result")
+    _len(result, 5, "result")
+    _same_device(ref, e_work, out, scale, result)
     ctx = _lib.context(dev)
     dptr = C.byref(dist) if dist is not None else None
     if pi0 is None:
@@ -104,8 +125,11 @@ def fixed_point_deep(residuals, weights, *, e_work=None, tol=1e-3, maxiter=40, r
         raise ValueError("residuals and weights must have the same length")
     if e_work is None:
         e_work = torch.empty(n, dtype=f32, device=residuals.device)
+    _len(_chk(e_work, f32, "e_work"), n, "e_work")
     if result is None:
         result = torch.empty(5, dtype=torch.float64, device=residuals.device)
+    _len(_chk(result, torch.float64, "result"), 5, "result")
+    _same_device(residuals, weights, e_work, result)
     ctx = _lib.context(dev)
     dptr = C.byref(dist) if dist is not None else None
     rc = ctx.lib.rlvi_fixed_point_deep_f32(ctx.handle, _p(residuals), _p(weights), _p(e_work), n, float(tol),
@@ -118,9 +142,11 @@ def shift_sum(losses, shift, c, *, pi_out=None, out=None):
     """rlvi_shift_sum_f64: out[0] = sum_i t_i/(c+t_i), t_i = exp(-l_i + shift) (rlvi.py:34-39)."""
     dev = _dev(losses)
     _chk(losses, torch.float64, "losses")
-    _chk(pi_out, torch.float64, "pi_out")
+    _len(_chk(pi_out, torch.float64, "pi_out"), losses.numel(), "pi_out")
     if out is None:
         out = torch.empty(1, dtype=torch.float64, device=losses.device)
+    _len(_chk(out, torch.float64, "out"), 1, "out")
+    _same_device(losses, pi_out, out)
     ctx = _lib.context(dev)
     rc = ctx.lib.rlvi_shift_sum_f64(ctx.handle, _p(losses), losses.numel(), float(shift), float(c), _p(pi_out),
                                     _p(out), _stream(dev))
@@ -132,9 +158,11 @@ def shift_sum_e(e, scale_t, c, *, pi_out=None, out=None):
     """rlvi_shift_sum_e_f64: out[0] = sum_i t_i/(c+t_i), t_i = e_i * scale_t (e = exp(-l), scale_t = exp(shift))."""
     dev = _dev(e)
     _chk(e, torch.float64, "e")
-    _chk(pi_out, torch.float64, "pi_out")
+    _len(_chk(pi_out, torch.float64, "pi_out"), e.numel(), "pi_out")
     if out is None:
         out = torch.empty(1, dtype=torch.float64, device=e.device)
+    _len(_chk(out, torch.float64, "out"), 1, "out")
+    _same_device(e, pi_out, out)
     ctx = _lib.context(dev)
     rc = ctx.lib.rlvi_shift_sum_e_f64(ctx.handle, _p(e), e.numel(), float(scale_t), float(c), _p(pi_out), _p(out),
                                       _stream(dev))
@@ -152,8 +180,16 @@ def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=
         raise ValueError("X must be [n, d]")
     n, d = X.shape
     _chk(params, f64, "params")
-    _chk(y, f64, "y")
-    _chk(weights, f64, "weights")
+    n_params = 1 + d + d * d if kind == LOSS_GAUSSIAN else d + (1 if intercept else 0)
+    if kind in (LOSS_SQDIST, LOSS_PCA, LOSS_GAUSSIAN) and intercept:
+        raise ValueError("this loss kind has no intercept")
+    _len(params, n_params, "params")
+    _len(_chk(y, f64, "y"), n, "y")
+    _len(_chk(weights, f64, "weights"), n, "weights")
+    _len(_chk(losses_out, f64, "losses_out"), n, "losses_out")
+    _len(_chk(e_out, f64, "e_out"), n, "e_out")
+    _len(_chk(wsum_out, f64, "wsum_out"), 2, "wsum_out")
+    _same_device(X, params, y, weights, losses_out, e_out, wsum_out)
     if want_losses and losses_out is None:
         losses_out = torch.empty(n, dtype=f64, device=X.device)
     if want_e and e_out is None:
@@ -173,12 +209,16 @@ def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, c
     dev = _dev(X)
     f64 = torch.float64
     _chk(X, f64, "X")
+    if X.dim() != 2:
+        raise ValueError("X must be [n, d]")
     n, d = X.shape
-    _chk(weights, f64, "weights")
-    _chk(y, f64, "y")
+    _len(_chk(weights, f64, "weights"), n, "weights")
+    _len(_chk(y, f64, "y"), n, "y")
     ctx = _lib.context(dev)
     if out is None:
         out = torch.zeros(ctx.lib.rlvi_moments_out_doubles(d), dtype=f64, device=X.device)
+    _len(_chk(out, f64, "out"), ctx.lib.rlvi_moments_out_doubles(d), "out")
+    _same_device(X, weights, y, out, center)
     if center is None:
         rc = ctx.lib.rlvi_weighted_moments_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
                                                1 if want_gram else 0, _p(out), _stream(dev))
@@ -203,12 +243,16 @@ def logistic_grad(X, y, weights, params, *, out=None):
     dev = _dev(X)
     f64 = torch.float64
     _chk(X, f64, "X")
+    if X.dim() != 2:
+        raise ValueError("X must be [n, d]")
     n, d = X.shape
-    _chk(y, f64, "y")
-    _chk(weights, f64, "weights")
-    _chk(params, f64, "params")
+    _len(_chk(y, f64, "y"), n, "y")
+    _len(_chk(weights, f64, "weights"), n, "weights")
+    _len(_chk(params, f64, "params"), d + 1, "params")
     if out is None:
         out = torch.empty(d + 1, dtype=f64, device=X.device)
+    _len(_chk(out, f64, "out"), d + 1, "out")
+    _same_device(X, y, weights, params, out)
     ctx = _lib.context(dev)
     rc = ctx.lib.rlvi_logistic_grad_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, _p(params), _p(out),
                                         _stream(dev))
@@ -222,11 +266,14 @@ def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=T
     dev = _dev(logits)
     f32 = torch.float32
     _chk(logits, f32, "logits")
+    if logits.dim() != 2:
+        raise ValueError("logits must be [batch, classes]")
     b, c = logits.shape
-    _chk(labels, torch.int64, "labels")
-    _chk(indexes, torch.int64, "indexes")
+    _len(_chk(labels, torch.int64, "labels"), b, "labels")
+    _len(_chk(indexes, torch.int64, "indexes"), b, "indexes")
     _chk(weights, f32, "weights")
     _chk(residuals, f32, "residuals")
+    _same_device(logits, labels, indexes, weights, residuals)
     n_train = weights.numel()
     if residuals.numel() != n_train:
         raise ValueError("residuals and weights must have the same length")
@@ -249,6 +296,8 @@ def fn_threshold(weights, alpha=0.05, prev_threshold=0.0, truncate=False, *, out
     _chk(weights, torch.float32, "weights")
     if out is None:
         out = torch.empty(1, dtype=torch.float32, device=weights.device)
+    _len(_chk(out, torch.float32, "out"), 1, "out")
+    _same_device(weights, out)
     ctx = _lib.context(dev)
     rc = ctx.lib.rlvi_fn_threshold_f32(ctx.handle, _p(weights), weights.numel(), float(alpha),
                                        float(prev_threshold), 1 if truncate else 0, _p(out), _stream(dev))

@@ -268,6 +268,22 @@ def test_c_abi_error_codes(dev):
                         torch.ones(2, device=dev), torch.zeros(2, device=dev))
     with pytest.raises(TypeError):
         ops.fixed_point(torch.zeros(4, dtype=torch.float64))               # CPU tensor: no CPU path
+    # lengths are checked on the host side (the C ABI sees raw pointers only)
+    X8 = X[:, :8].contiguous()
+    v8, v7 = torch.ones(8, dtype=torch.float64, device=dev), torch.ones(7, dtype=torch.float64, device=dev)
+    with pytest.raises(ValueError, match="weights must have 8"):
+        ops.weighted_moments(X8, v7)
+    with pytest.raises(ValueError, match="params must have 9"):
+        ops.loss(ops.LOSS_LOGISTIC_CE, X8, v8, y=v8, intercept=True)
+    with pytest.raises(ValueError, match="params must have 73"):
+        ops.loss(ops.LOSS_GAUSSIAN, X8, v8)
+    with pytest.raises(ValueError, match="y must have 8"):
+        ops.logistic_grad(X8, v7, v8, torch.zeros(9, dtype=torch.float64, device=dev))
+    with pytest.raises(ValueError, match="out must have 4"):
+        ops.fixed_point(x, out=v7)
+    with pytest.raises(ValueError, match="labels must have 2"):
+        ops.wce_fwd_bwd(torch.zeros((2, 10), device=dev), torch.zeros(3, dtype=torch.int64, device=dev),
+                        torch.ones(2, device=dev), torch.zeros(2, device=dev))
     # the library is still healthy afterwards
     pi, _ = ops.fixed_point(torch.rand(100, dtype=torch.float64, device=dev))
     assert torch.isfinite(pi).all()
