@@ -102,8 +102,8 @@ def check(rc, what):
 
 
 class Context:
-    """One rlvi_ctx per (device); owns the library's device scratch.  Not thread-safe: use one
-    context per host thread / stream."""
+    """One rlvi_ctx per (device, stream); owns the library's device scratch.  Calls on one context must be
+    stream-ordered (include/rlvi_b200.h, Conventions), so `context()` hands out one per CUDA stream."""
 
     def __init__(self, device: int):
         self.lib = load()
@@ -132,8 +132,18 @@ class Context:
 _contexts: dict = {}
 
 
-def context(device: int) -> Context:
-    ctx = _contexts.get(device)
+def context(device: int, stream: int = 0) -> Context:
+    """The context of (device, stream handle); stream 0 = the legacy default stream (torch's default)."""
+    key = (int(device), int(stream or 0))
+    ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[device] = Context(device)
+        with _lock:
+            ctx = _contexts.get(key)
+            if ctx is None:
+                ctx = _contexts[key] = Context(device)
     return ctx
+
+
+def launches(device: int) -> int:
+    """Kernels launched by the library on `device`, over all its contexts."""
+    return sum(c.launches for (d, _), c in list(_contexts.items()) if d == int(device))

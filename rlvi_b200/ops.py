@@ -61,9 +61,15 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _ctx(dev):
+    """The library context of torch's CURRENT stream on `dev`: contexts own scratch, so each stream has
+    its own and calls issued from different streams never share it."""
+    return _lib.context(dev, torch.cuda.current_stream(dev).cuda_stream)
+
+
 def launch_count(device=0) -> int:
-    """Kernels launched by the library on `device` since its context was created."""
-    return _lib.context(int(device)).launches
+    """Kernels launched by the library on `device` since its contexts were created."""
+    return _lib.launches(int(device))
 
 
 def read_result(result: torch.Tensor) -> dict:
@@ -101,7 +107,7 @@ def fixed_point(losses=None, *, e_work=None, scale=None, variant=FP_STANDARD, to
     _chk(result, f64, "result")
     _len(result, 5, "result")
     _same_device(ref, e_work, out, scale, result)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     dptr = C.byref(dist) if dist is not None else None
     if pi0 is None:
         rc = ctx.lib.rlvi_fixed_point_f64(ctx.handle, int(variant), _p(losses), _p(scale), _p(e_work), n, float(tol),
@@ -130,7 +136,7 @@ def fixed_point_deep(residuals, weights, *, e_work=None, tol=1e-3, maxiter=40, r
         result = torch.empty(5, dtype=torch.float64, device=residuals.device)
     _len(_chk(result, torch.float64, "result"), 5, "result")
     _same_device(residuals, weights, e_work, result)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     dptr = C.byref(dist) if dist is not None else None
     rc = ctx.lib.rlvi_fixed_point_deep_f32(ctx.handle, _p(residuals), _p(weights), _p(e_work), n, float(tol),
                                            int(maxiter), _p(result), dptr, _stream(dev))
@@ -147,7 +153,7 @@ def shift_sum(losses, shift, c, *, pi_out=None, out=None):
         out = torch.empty(1, dtype=torch.float64, device=losses.device)
     _len(_chk(out, torch.float64, "out"), 1, "out")
     _same_device(losses, pi_out, out)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_shift_sum_f64(ctx.handle, _p(losses), losses.numel(), float(shift), float(c), _p(pi_out),
                                     _p(out), _stream(dev))
     _lib.check(rc, "rlvi_shift_sum_f64")
@@ -163,7 +169,7 @@ def shift_sum_e(e, scale_t, c, *, pi_out=None, out=None):
         out = torch.empty(1, dtype=torch.float64, device=e.device)
     _len(_chk(out, torch.float64, "out"), 1, "out")
     _same_device(e, pi_out, out)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_shift_sum_e_f64(ctx.handle, _p(e), e.numel(), float(scale_t), float(c), _p(pi_out), _p(out),
                                       _stream(dev))
     _lib.check(rc, "rlvi_shift_sum_e_f64")
@@ -196,7 +202,7 @@ def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=
         e_out = torch.empty(n, dtype=f64, device=X.device)
     if weights is not None and wsum_out is None:
         wsum_out = torch.empty(2, dtype=f64, device=X.device)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_loss_f64(ctx.handle, int(kind), 1 if intercept else 0, _p(X), _p(y), n, d, _p(params),
                                _p(weights), _p(losses_out), _p(e_out), _p(wsum_out), _stream(dev))
     _lib.check(rc, "rlvi_loss_f64")
@@ -214,7 +220,7 @@ def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, c
     n, d = X.shape
     _len(_chk(weights, f64, "weights"), n, "weights")
     _len(_chk(y, f64, "y"), n, "y")
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     if out is None:
         out = torch.zeros(ctx.lib.rlvi_moments_out_doubles(d), dtype=f64, device=X.device)
     _len(_chk(out, f64, "out"), ctx.lib.rlvi_moments_out_doubles(d), "out")
@@ -253,7 +259,7 @@ def logistic_grad(X, y, weights, params, *, out=None):
         out = torch.empty(d + 1, dtype=f64, device=X.device)
     _len(_chk(out, f64, "out"), d + 1, "out")
     _same_device(X, y, weights, params, out)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_logistic_grad_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, _p(params), _p(out),
                                         _stream(dev))
     _lib.check(rc, "rlvi_logistic_grad_f64")
@@ -283,7 +289,7 @@ def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=T
     dlogits = torch.empty_like(logits) if want_grad else None
     per = torch.empty(b, dtype=f32, device=logits.device) if want_per_sample else None
     correct = torch.empty(2, dtype=torch.int32, device=logits.device) if want_correct else None
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_wce_fwd_bwd_f32(ctx.handle, _p(logits), _p(labels), _p(indexes), _p(weights), _p(residuals), b,
                                       c, n_train, _p(per), _p(dlogits), _p(out_loss), _p(correct), _stream(dev))
     _lib.check(rc, "rlvi_wce_fwd_bwd_f32")
@@ -298,7 +304,7 @@ def fn_threshold(weights, alpha=0.05, prev_threshold=0.0, truncate=False, *, out
         out = torch.empty(1, dtype=torch.float32, device=weights.device)
     _len(_chk(out, torch.float32, "out"), 1, "out")
     _same_device(weights, out)
-    ctx = _lib.context(dev)
+    ctx = _ctx(dev)
     rc = ctx.lib.rlvi_fn_threshold_f32(ctx.handle, _p(weights), weights.numel(), float(alpha),
                                        float(prev_threshold), 1 if truncate else 0, _p(out), _stream(dev))
     _lib.check(rc, "rlvi_fn_threshold_f32")
