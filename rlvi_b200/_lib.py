@@ -39,7 +39,7 @@ class FpDist(C.Structure):
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()       # re-entrant: context() -> Context() -> load()
 
 
 def load():
@@ -137,6 +137,7 @@ def context(device: int, stream: int = 0) -> Context:
     key = (int(device), int(stream or 0))
     ctx = _contexts.get(key)
     if ctx is None:
+        load()
         with _lock:
             ctx = _contexts.get(key)
             if ctx is None:

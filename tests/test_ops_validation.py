@@ -173,3 +173,21 @@ def test_contexts_are_per_device_and_stream(monkeypatch):
     assert b is not a and c is not a and _lib.context(0, 0x7f00) is b
     assert made == [0, 0, 1]
     assert _lib.launches(0) == 6 and _lib.launches(1) == 3 and _lib.launches(2) == 0
+
+
+def test_first_context_call_loads_the_library_without_deadlock():
+    """context() holds the module lock while it builds a Context, whose constructor calls load(): with a
+    cold module (library not loaded yet) that must not self-deadlock.  Runs in a child process with a
+    timeout; without a GPU the expected outcome is the loud rlvi_ctx_create failure, not a hang."""
+    import subprocess
+    import sys
+    code = ("import rlvi_b200._lib as L\n"
+            "assert L._lib is None\n"
+            "try:\n"
+            "    L.context(0)\n"
+            "    print('created')\n"
+            "except L.RlviError as e:\n"
+            "    print('refused:', e)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "created" in r.stdout or "refused" in r.stdout
