@@ -42,6 +42,40 @@ def pi_tol(ref_pi):
     return max(F64_TOL, 8 * 2.0 ** -52 / max(float(np.mean(ref_pi)), 1e-300))
 
 
+def test_concurrent_streams_use_separate_contexts(dev):
+    """include/rlvi_b200.h, Conventions: calls on ONE context must be stream-ordered; the binding keeps one
+    context per (device, stream), so work issued from two torch streams may overlap on the GPU and still
+    gives the bits of the same calls made alone on the default stream."""
+    from rlvi_b200 import _lib, ops, synth
+    n, d = 300001, 64
+    data = []
+    for seed in (11, 12):
+        X, y, theta = synth.logistic_data(n, d, seed=seed)
+        params = np.concatenate([[0.1 * seed], theta])
+        data.append(tuple(cu(a, dev) for a in (X, y, params)))
+
+    def step(X, y, params):
+        _, e, _ = ops.loss(ops.LOSS_LOGISTIC_CE, X, params, y=y, intercept=True, want_losses=False, want_e=True)
+        pi, res = ops.fixed_point(None, e_work=e)
+        return pi, res, ops.weighted_moments(X, pi, y=y)
+
+    alone = [step(*t) for t in data]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in data]
+    outs = [None, None]
+    for rep in range(3):
+        for k, (st, t) in enumerate(zip(streams, data)):
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                outs[k] = step(*t)
+    torch.cuda.synchronize()
+    handles = {st.cuda_stream for st in streams}
+    assert len(handles) == 2 and all((dev.index, h) in _lib._contexts for h in handles)
+    for (pi0, res0, mom0), (pi1, res1, mom1) in zip(alone, outs):
+        assert torch.equal(pi0, pi1) and torch.equal(mom0, mom1)
+        assert ops.read_result(res0) == ops.read_result(res1)
+
+
 # ==================================================================================================
 # E-step: fixed point
 # ==================================================================================================
