@@ -13,8 +13,9 @@ label corruption, synthetic, generated on the device.  One STEP = one E+M pass o
                                                   (tol 1e-3, maxiter 100) fires, then writes pi
   (3) statistics     rlvi_weighted_moments_f64    reads X, pi -> S0, X^T pi, X^T Pi X  (+ all-reduce, N > 1)
 N > 1 shards the samples (strong scaling: the same 2^26 samples over N GPUs); the fixed point exchanges its
-three partial sums per pass inside the kernel over NVLink peer memory, the statistics are all-reduced by NCCL.
-Prints ONE JSON line (rank 0).
+three partial sums per pass inside the kernel over NVLink peer memory, and the d x d statistics are summed by a
+small kernel over the same peer windows (rlvi_stats_allreduce_f64; NCCL only carries the set-up and the timing
+reductions).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
