@@ -109,9 +109,10 @@ class ShardGroup:
         if (self.window is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
                 and t.numel() <= self.STATS_CAPACITY):
             d = self.stats_dist()
-            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(self._ctx.lib.rlvi_stats_allreduce_f64(self._ctx.handle, C.c_void_p(t.data_ptr()), t.numel(),
-                                                              C.byref(d), stream), "rlvi_stats_allreduce_f64")
+            handle = torch.cuda.current_stream(self.device).cuda_stream
+            ctx = _lib.context(self.device.index, handle)       # the launching stream's own context (scratch)
+            _lib.check(ctx.lib.rlvi_stats_allreduce_f64(ctx.handle, C.c_void_p(t.data_ptr()), t.numel(), C.byref(d),
+                                                        C.c_void_p(handle)), "rlvi_stats_allreduce_f64")
             return t
         td.all_reduce(t, op=td.ReduceOp.SUM)
         return t
