@@ -34,6 +34,20 @@ METRIC = "rlvi_em_step_samples_per_sec"
 UNIT = "samples/s"
 
 
+def claim_stdout():
+    """Reserve the process's stdout for the ONE JSON line: fd 1 is re-pointed at stderr for everything else
+    (NCCL prints its version banner to stdout when NCCL_DEBUG is set, as it is on the GPU boxes)."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+def emit(out, line):
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,7 +148,7 @@ def workload_config(args, world):
             "parallelism": f"sample-sharded dp{world}"}
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,13 +162,13 @@ def run_reference(args):
                            sample=f"each step runs a bounded sample: N=2^{args.cpu_log2n} rows of the same workload"),
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(out, line)
 
 
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
-def run_b200(args):
+def run_b200(args, out):
     import numpy as np
     import torch
 
@@ -312,7 +326,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_em_step_bench(args.cpu_log2n, d, 1, 1)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(out, line)
     if world > 1:
         group.close()
         torch.distributed.destroy_process_group()
@@ -394,10 +408,11 @@ def run_e2e(args, X, y, params, dev, world, rank, n_total, group):
 
 def main():
     args = parse_args()
+    out = claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out)
     else:
-        run_b200(args)
+        run_b200(args, out)
 
 
 if __name__ == "__main__":

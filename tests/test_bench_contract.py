@@ -54,3 +54,17 @@ def test_both_arms_report_the_same_config_keys():
     """The driver compares the two arms: same metric / unit / workload string."""
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert src.count("workload_config(args") >= 2        # both arms build `config` from the same function
+
+
+def test_stdout_carries_only_the_json_line():
+    """Libraries that write to fd 1 (NCCL's version banner under NCCL_DEBUG) must not reach stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "out = bench.claim_stdout()\n"
+            "os.write(1, b'NCCL version x.y\\n'); print('python noise')\n"
+            "bench.emit(out, {'metric': 'm', 'value': 1})\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"metric": "m", "value": 1}\n'
+    assert "NCCL version x.y" in r.stderr and "python noise" in r.stderr
+    r = run(["--impl", "reference", "--cpu-log2n", "12", "--steps", "1", "--warmup", "0"])
+    assert r.returncode == 0 and len(r.stdout.splitlines()) == 1 and r.stdout.startswith("{")
