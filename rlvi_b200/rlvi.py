@@ -118,17 +118,25 @@ def mean(sample, maxiter=100, tol=1e-3):
     return to_caller(theta, was_np)
 
 
-def _gpu_sym_solve(G, b):
+def _gpu_sym_solve(G, b, n):
     """theta = argmin ||sqrt(Pi) (X theta - y)||.  The reference calls scipy lstsq (LAPACK gelsd) on the
     N x d scaled design (rlvi.py:71,80); this is the same minimiser from the d x d statistics
-    G = X^T Pi X, b = X^T Pi y: Cholesky when G is positive definite, else an eigen-decomposition
-    pseudo-inverse so that rank-deficient designs give the minimum-norm solution as gelsd does."""
+    G = X^T Pi X, b = X^T Pi y: Cholesky when G is numerically positive definite, else an eigen-decomposition
+    pseudo-inverse so that rank-deficient designs give the minimum-norm solution as gelsd does.  A summed Gram
+    matrix carries rounding noise of about eps * (d + sqrt(n)) * lambda_max in its null directions, so that
+    (not gelsd's eps * sigma_max on the design itself) is the rank threshold: pivots / eigenvalues below it
+    are noise, not signal."""
+    d = G.shape[0]
+    rtol = torch.finfo(G.dtype).eps * (d + math.sqrt(n))
     L, info = torch.linalg.cholesky_ex(G)
-    if int(info) == 0:                       # the usual case: G is positive definite
+    # pivot_i / G_ii = the share of feature i not explained by features < i: scale-free, so badly scaled
+    # but independent features still take the Cholesky path
+    resid = torch.diagonal(L) ** 2 / torch.diagonal(G)
+    if int(info) == 0 and bool(resid.min() > rtol):          # the usual case
         return torch.cholesky_solve(b.unsqueeze(1), L)[:, 0]
-    evals, evecs = torch.linalg.eigh(G)      # rank-deficient design: minimum-norm solution, gelsd's rcond rule
-    cutoff = torch.finfo(G.dtype).eps * evals.abs().max()
-    inv = torch.where(evals.abs() > cutoff, 1.0 / evals, torch.zeros_like(evals))
+    evals, evecs = torch.linalg.eigh(G)      # rank-deficient design: minimum-norm solution
+    cutoff = rtol * evals.abs().max()
+    inv = torch.where(evals > cutoff, 1.0 / evals, torch.zeros_like(evals))
     return evecs @ (inv * (evecs.T @ b))
 
 
@@ -146,7 +154,7 @@ def linear_regression(X, y, maxiter=100, tol=1e-3):
         nonlocal mom
         mom = ops.weighted_moments(Xd, pi, y=yd, out=mom)
         m = ops.split_moments(mom, d)
-        theta = _gpu_sym_solve(m["G"], m["Sy"])                  # rlvi.py:70-71,79-80
+        theta = _gpu_sym_solve(m["G"], m["Sy"], n)                  # rlvi.py:70-71,79-80
         _, _, wsum = ops.loss(ops.LOSS_SQRES, Xd, theta, y=yd, weights=pi, losses_out=r2)   # rlvi.py:72-73
         return theta, wsum
 

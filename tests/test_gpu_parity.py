@@ -569,6 +569,24 @@ def test_linear_regression_golden(dev, tag):
     assert relmax(rlvi.linear_regression(g["X"], g["y"]), g["theta"]) < F64_TOL
 
 
+def test_linear_regression_rank_deficient_and_badly_scaled(dev):
+    """rlvi.py:71 solves with lstsq (gelsd): a duplicated column gets the minimum-norm solution; columns whose
+    scales differ by 1e7 are still full rank.  The Gram route must agree in both cases."""
+    from rlvi_b200 import rlvi
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(200, 4))
+    X = np.hstack([X, X[:, :1]])
+    y = X @ np.array([1.0, -2.0, 0.5, 3.0, 1.0]) + 0.01 * rng.normal(size=200)
+    got = rlvi.linear_regression(X, y)
+    assert relmax(got, rlvi_np.linear_regression(X, y)) < 1e-6
+    assert abs(got[0] - got[4]) < 1e-8 * abs(got[0])
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(300, 4)) * np.array([1.0, 1e-7, 1e3, 1.0])
+    y = X @ np.array([1.0, 2e7, -3e-3, 0.5]) + 0.1 * rng.normal(size=300)
+    ref = rlvi_np.linear_regression(X, y)
+    assert np.max(np.abs(rlvi.linear_regression(X, y) - ref) / np.abs(ref)) < 1e-6
+
+
 def test_mm_log_reg_and_logistic_regression_golden(dev):
     from rlvi_b200 import rlvi, utils
     g = load_golden("mm_log_reg_n768_d64")
