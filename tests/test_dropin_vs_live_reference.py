@@ -99,3 +99,38 @@ def test_deep_and_online_functions(mods, seed):
     assert np.array_equal(ours, ref)
     assert relmax(online.update_weights_rlvi(ours), O.update_weights_rlvi(ref)) < 1e-13
     assert relmax(online.update_weights_rlvi(ours, 1e-5, 7), O.update_weights_rlvi(ref, 1e-5, 7)) < 1e-13
+
+
+def test_input_conventions_and_degenerate_designs(mods):
+    """What NumPy callers may pass (lists, integer / float32 / Fortran-ordered arrays) and the designs lstsq
+    handles silently (more features than samples, a zero column): same answers as the reference."""
+    rlvi, utils, _, _ = mods
+    R, RU = ref_shim.standard()
+    rng = np.random.default_rng(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X, y = rng.normal(size=(6, 10)), rng.normal(size=6)                  # underdetermined: minimum norm
+        assert relmax(rlvi.linear_regression(X, y), R.linear_regression(X.copy(), y.copy())) < 1e-10
+        X = rng.normal(size=(100, 4))
+        X[:, 2] = 0                                                         # zero column
+        y = X @ np.array([1.0, 2.0, 0.0, -1.0]) + 0.1 * rng.normal(size=100)
+        assert relmax(rlvi.linear_regression(X, y), R.linear_regression(X.copy(), y.copy())) < 1e-10
+        Xi = rng.integers(-5, 5, size=(50, 3))
+        yi = Xi @ np.array([1, 2, 3]) + rng.integers(-1, 2, size=50)
+        assert relmax(rlvi.linear_regression(Xi, yi), R.linear_regression(Xi.copy(), yi.copy())) < 1e-10
+        losses = np.abs(rng.normal(size=30))
+        assert relmax(rlvi.update_weights(list(losses)), R.update_weights(losses.copy())) < 1e-13
+        assert relmax(rlvi.update_weights(losses, maxiter=1), R.update_weights(losses.copy(), maxiter=1)) < 1e-13
+        assert relmax(rlvi.update_weights(losses, tol=10.0), R.update_weights(losses.copy(), tol=10.0)) < 1e-13
+        X32 = rng.normal(size=(50, 3)).astype(np.float32)
+        ours = rlvi.mean(X32)
+        assert ours.dtype == np.float64 and relmax(ours, R.mean(X32.copy())) < 1e-12
+        Xf = np.asfortranarray(rng.normal(size=(80, 4)))
+        yf = Xf @ np.ones(4) + rng.normal(size=80)
+        assert relmax(rlvi.linear_regression(Xf, yf), R.linear_regression(Xf.copy(), yf.copy())) < 1e-10
+        same = np.full((20, 2), 3.0)                                         # sigma2 = 0: NaN on both sides (Q1)
+        assert np.isnan(rlvi.mean(same)).all() and np.isnan(R.mean(same.copy())).all()
+        Xc = rng.normal(size=(120, 3))
+        for eps in (0.0, 0.05, 0.6):
+            assert relmax(rlvi.covariance(Xc, eps), R.covariance(Xc.copy(), eps)) < 1e-6
+        assert relmax(utils.sigmoid(Xc), RU.sigmoid(Xc)) < 1e-15             # any shape
