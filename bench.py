@@ -317,6 +317,12 @@ def run_b200(args, out):
         k32_ms = float(t)
     line["fixed_k32"] = {"fixed_point_passes": 32, "ms_per_step": k32_ms, "value": n_total / (k32_ms * 1e-3), "steps": 5}
 
+    # ---- what a full logistic M-step adds to the step (timed and reported separately) --
+    try:
+        line["m_step_extras"] = m_step_extras(X, y, pi, params, mom, d)
+    except Exception as exc:       # reporting only: never lose the headline line to it
+        line["m_step_extras"] = {"error": repr(exc)[:200]}
+
     # ---- e2e: the same step through the host-buffer C-ABI call, H2D/D2H inside the timed region --------
     if not args.no_e2e:
         line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total, group)
@@ -330,6 +336,46 @@ def run_b200(args, out):
     if world > 1:
         group.close()
         torch.distributed.destroy_process_group()
+
+
+def m_step_extras(X, y, pi, params, mom, d):
+    """The pieces of utils.mm_log_reg (utils.py:32-58) that are not part of the E+M step: one gradient pass
+    X^T (pi (sigmoid - y)) over this rank's shard (the MM loop runs J of them), and the (d+1) x (d+1) inverse of the
+    majoriser built from the step's statistics.  Rank-local (no collective), CUDA events, mean of 5."""
+    import torch
+
+    from rlvi_b200 import ops
+
+    dev = X.device
+    n = X.shape[0]
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    g = torch.empty(d + 1, dtype=torch.float64, device=dev)
+    t_grad = timed(lambda: ops.logistic_grad(X, y, pi, params, out=g))
+    m = ops.split_moments(mom, d)
+    A = torch.empty((d + 1, d + 1), dtype=torch.float64, device=dev)
+    A[0, 0] = m["S0"]
+    A[0, 1:] = m["S1"]
+    A[1:, 0] = m["S1"]
+    A[1:, 1:] = m["G"]
+    A = A / A.diagonal().max()                       # scale-free: the collapse regime makes the entries tiny
+    t_inv = timed(lambda: torch.linalg.inv(0.25 * A))
+    grad_bytes = n * (d * 8 + 8 + 8)
+    return {"logistic_grad_pass_ms": t_grad, "logistic_grad_GBps": grad_bytes / (t_grad * 1e-3) / 1e9,
+            "logistic_grad_algorithmic_bytes": int(grad_bytes), "majoriser_inverse_ms": t_inv,
+            "note": "rlvi_logistic_grad_f64 over this rank's shard (one of the J passes of utils.mm_log_reg) and "
+                    "torch.linalg.inv of the (d+1)^2 majoriser on the device; not included in `value`"}
 
 
 def pin_to_gpu_cpus(index):
