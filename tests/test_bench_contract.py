@@ -68,3 +68,35 @@ def test_stdout_carries_only_the_json_line():
     assert "NCCL version x.y" in r.stderr and "python noise" in r.stderr
     r = run(["--impl", "reference", "--cpu-log2n", "12", "--steps", "1", "--warmup", "0"])
     assert r.returncode == 0 and len(r.stdout.splitlines()) == 1 and r.stdout.startswith("{")
+
+
+def test_m_step_extras_report(monkeypatch):
+    """bench.py's separately-timed M-step pieces: keys, byte count, and that they are computed
+    from the step's own statistics buffer -- run with the kernels replaced by the test double and mocked CUDA events."""
+    sys.path.insert(0, ROOT)
+    import abi_double
+    import bench
+    from rlvi_b200 import ops
+
+    class Ev:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 10.0
+
+    abi_double.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    n, d = 500, 8
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(n, d, dtype=torch.float64, generator=g)
+    y = (torch.rand(n, generator=g) < 0.5).double()
+    pi = torch.rand(n, dtype=torch.float64, generator=g) * 1e-7          # collapse-regime magnitudes
+    out = bench.m_step_extras(X, y, pi, torch.zeros(d + 1, dtype=torch.float64), ops.weighted_moments(X, pi), d)
+    assert out["logistic_grad_pass_ms"] == 2.0 and out["majoriser_inverse_ms"] == 2.0      # 10 ms / 5 repetitions
+    assert out["logistic_grad_algorithmic_bytes"] == n * (d * 8 + 16)
+    assert abs(out["logistic_grad_GBps"] - n * (d * 8 + 16) / 2e-3 / 1e9) < 1e-9
