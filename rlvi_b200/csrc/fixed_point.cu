@@ -13,10 +13,11 @@
 // redundantly by every block from the same bits, in the reference's FP64 operation order, so the
 // loop exits on the device without a host round trip.  A final pass writes pi.
 //
-// Cross-block reduction is deterministic: block partials -> grid barrier -> every block sums the
-// partials in the same fixed order.  With `dist` set, block 0 then stores the rank's totals into
-// every peer's inbox over NVLink and all blocks sum the `world` slots of their own inbox in rank
-// order, so every rank sees identical totals (same stop decision everywhere).
+// Cross-block reduction is deterministic and single-hop: block partials -> the LAST-arriving block
+// sums them in block order and publishes the rank's totals + a sequence tag (to a local window, or
+// with `dist` set to every peer's inbox over NVLink) -> all blocks poll their own window for the tags
+// (which is the grid barrier) and add the `world` slots in rank order, so every block of every rank
+// sees identical totals and takes the same stop decision.
 #include <math.h>
 #include <stdlib.h>
 
