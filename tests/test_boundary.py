@@ -141,6 +141,45 @@ def test_product_never_imports_the_oracle():
             assert not any(n.split(".")[0] == "oracle" for n in names), fn
 
 
+def _oracle_import_sites(path):
+    """(function name or '<module>', line) of every `import oracle...` / `from oracle... import` in a file."""
+    tree = ast.parse(open(path).read())
+    sites = []
+
+    def walk(node, scope):
+        for child in ast.iter_child_nodes(node):
+            s = child.name if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef)) else scope
+            names = []
+            if isinstance(child, ast.Import):
+                names = [a.name for a in child.names]
+            elif isinstance(child, ast.ImportFrom):
+                names = [child.module or ""]
+            if any(n.split(".")[0] == "oracle" for n in names):
+                sites.append((scope, child.lineno))
+            walk(child, s)
+
+    walk(tree, "<module>")
+    return sites
+
+
+def test_oracle_is_only_used_as_the_checker():
+    """Outside tests/ and oracle/ itself, the oracle may be imported in exactly two places: __graft_entry__.smoke()
+    (the on-device check) and bench.py's CPU leg (cpu_baseline / --impl reference).  Tools, the package and the B200
+    arm of the bench never touch it."""
+    allowed = {("__graft_entry__.py", "smoke"), ("bench.py", "cpu_em_step_bench")}
+    found = set()
+    for dirpath, dirnames, filenames in os.walk(ROOT):
+        rel = os.path.relpath(dirpath, ROOT)
+        dirnames[:] = [d for d in dirnames if d not in (".git", "gpurun_out", "__pycache__", "baseline")
+                       and not (rel == "." and d in ("tests", "oracle"))]
+        for fn in filenames:
+            if fn.endswith(".py"):
+                path = os.path.join(dirpath, fn)
+                for scope, _ in _oracle_import_sites(path):
+                    found.add((os.path.relpath(path, ROOT), scope))
+    assert found == allowed, found
+
+
 # ---- reference signatures (SURVEY.md section 8b) ---------------------------------------------------
 def sig(f):
     return [(p.name, p.default) for p in inspect.signature(f).parameters.values()]
