@@ -12,7 +12,9 @@ label corruption, synthetic, generated on the device.  One STEP = one E+M pass o
   (2) E-step         rlvi_fixed_point_f64         K_fp passes over e until the reference's stop rule
                                                   (tol 1e-3, maxiter 100) fires, then writes pi
   (3) statistics     rlvi_weighted_moments_f64    reads X, pi -> S0, X^T pi, X^T Pi X  (+ all-reduce, N > 1)
-N > 1 shards the samples (strong scaling: the same 2^26 samples over N GPUs); the fixed point exchanges its
+N > 1 shards the samples (strong scaling: the same 2^26 samples over N GPUs -- every block of 2^20 global rows is
+drawn from its own seeded generator, rlvi_b200.synth.logistic_rows_torch, so 1, 2, 4 and 8 ranks process identical
+data and the `fixed_point` / `stats_checksum` blocks of their lines can be compared); the fixed point exchanges its
 three partial sums per pass inside the kernel over NVLink peer memory, and the d x d statistics are summed by a
 small kernel over the same peer windows (rlvi_stats_allreduce_f64; NCCL only carries the set-up and the timing
 reductions).  Prints ONE JSON line (rank 0).
@@ -60,6 +62,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (configs 2b, 3, 4, 5; N = 1 only)")
+    ap.add_argument("--config3-log2n", type=int, default=24)
     return ap.parse_args()
 
 
@@ -114,30 +118,50 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference's E+M step (reference is pure Python/NumPy)
 # --------------------------------------------------------------------------------------------------
-def cpu_em_step_bench(log2n, d, steps, warmup):
+def force_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must use every host core whatever the
+    launcher did.  Called BEFORE NumPy is imported (bench.py imports it lazily), and again through threadpoolctl."""
+    n = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = str(n)
+    return n
+
+
+def cpu_em_step_bench(log2n, d, steps, warmup, keep=False):
+    ncpu = force_host_threads()
     import numpy as np
     from oracle import rlvi_np
     from rlvi_b200 import synth
 
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=ncpu)
         blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
         blas_threads = 1
     n = 1 << log2n
     X, y, theta = synth.logistic_data(n, d, seed=0)
     params = np.concatenate([[0.0], theta])
-    iters = None
+    ref = None
     for _ in range(warmup):
-        iters = rlvi_np.em_step_logistic(X, y, params)["iters"]
+        ref = rlvi_np.em_step_logistic(X, y, params)
     t0 = time.perf_counter()
     for _ in range(steps):
-        iters = rlvi_np.em_step_logistic(X, y, params)["iters"]
+        ref = rlvi_np.em_step_logistic(X, y, params)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": n / dt, "unit": UNIT, "cores": int(blas_threads), "kind": "port",
-            "sample": f"oracle.rlvi_np.em_step_logistic (NumPy restatement of rlvi.py:8-20 + utils.py:19-21,36-38) on "
-                      f"N=2^{log2n} x d={d} FP64 of the same synthetic workload, {steps} step(s) of {dt:.2f} s, "
-                      f"{iters} fixed-point passes; BLAS threads={blas_threads}, os.cpu_count()={os.cpu_count()}"}, dt
+    iters = ref["iters"]
+    cb = {"value": n / dt, "unit": UNIT, "cores": int(blas_threads), "kind": "port",
+          "sample": f"oracle.rlvi_np.em_step_logistic (NumPy restatement of rlvi.py:8-20 + utils.py:19-21,36-38) on "
+                    f"N=2^{log2n} x d={d} FP64 of the same synthetic workload, {steps} step(s) of {dt:.2f} s, "
+                    f"{iters} fixed-point passes; BLAS threads={blas_threads}, os.cpu_count()={os.cpu_count()}"}
+    if keep:
+        # the CPU side of `e2e_call`: the oracle's whole EM loop (rlvi.py:92-108 with utils.mm_log_reg) on the same
+        # arrays, timed here so that the oracle is only ever touched by this CPU leg
+        t0 = time.perf_counter()
+        th_ref = rlvi_np.logistic_regression_mm(X, y)
+        t_loop = time.perf_counter() - t0
+        return cb, dt, (X, y, params, ref, th_ref, t_loop)
+    return cb, dt
 
 
 def workload_config(args, world):
@@ -152,6 +176,7 @@ def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    force_host_threads()                      # before NumPy loads its BLAS: torchrun exports OMP_NUM_THREADS=1
     steps = max(1, min(args.steps, 5))
     warmup = 1 if args.warmup > 0 else 0
     cb, dt = cpu_em_step_bench(args.cpu_log2n, args.d, steps, warmup)
@@ -189,9 +214,7 @@ def run_b200(args, out):
     d = args.d
     lo, hi = rdist.shard_bounds(n_total, rank, world)
     n = hi - lo
-    X, y, theta = synth.logistic_shard_torch(n, d, dev, seed=1234 + rank)
-    if world > 1:                                    # every rank needs the same theta*
-        torch.distributed.broadcast(theta, 0)
+    X, y, theta = synth.logistic_rows_torch(lo, hi, d, dev, seed=1234)      # a function of the GLOBAL row index
     params = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), theta]).contiguous()
     e = torch.empty(n, dtype=torch.float64, device=dev)
     pi = torch.empty(n, dtype=torch.float64, device=dev)
@@ -267,6 +290,10 @@ def run_b200(args, out):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
                 "step_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak,   # per GPU
+                "peak_nominal": 8000.0, "frac_nominal": kernels[dom]["GBps"] / 8000.0,
+                "step_frac_nominal": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / 8000.0,
+                "note": "fractions against BOTH denominators (SURVEY.md H7): `peak` = measured copy bandwidth, "
+                        "`peak_nominal` = the ~8 TB/s BASELINE.json's north_star names",
                 "kernels": kernels}
     # the statistics pass is bounded by the FP64 tensor pipe, not by HBM: report that too
     gram_flops = n * 36 * 512 / 4          # 36 DMMA.8x8x4 (512 flop) per 4 rows
@@ -274,6 +301,9 @@ def run_b200(args, out):
                                "unit": "TFLOP/s", "frac": gram_flops / (kms[2] * 1e-3) / 1e12 / 36.9,
                                "peak_source": "measured DMMA.8x8x4 issue rate, tools/ubench_dmma.cu "
                                               "(profiles/r01_ubench_dmma.txt); not in MEASURED_PEAKS.json"}
+    line_extra = {"measured_fp64_tflops": {"value": 36.9, "unit": "TFLOP/s", "what": "DMMA.8x8x4 issue-rate peak of this GPU "
+                                           "model (4.0 clk per instruction per SM at 1.965 GHz x 148 SMs)",
+                                           "source": "tools/ubench_dmma.cu run under gpurun, profiles/r01_ubench_dmma.txt"}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -290,6 +320,13 @@ def run_b200(args, out):
             "fixed_point": {k: fp[k] for k in ("eps", "iters", "converged", "sum_pi")},
             "host": {"cpus": os.cpu_count(), "inter_step_gap_ms": float(np.mean(gaps)) if gaps else 0.0,
                      "cpus_local_to_gpu": numa}}
+    line.update(line_extra)
+    # the step's (all-reduced) statistics, normalised: identical data on every world size => comparable across N
+    mh = ops.split_moments(mom, d)
+    line["stats_checksum"] = {"trace_G_over_S0": float(torch.trace(mh["G"]) / mh["S0"]),
+                              "sum_abs_G_over_S0": float(mh["G"].abs().sum() / mh["S0"]),
+                              "S0": float(mh["S0"]),
+                              "note": "same 2^%d global samples at every N (seeded per 2^20-row block)" % args.log2n}
 
     # ---- comparable-across-runs variant: exactly 32 fixed-point passes ---------------
     def step_k32():
@@ -328,14 +365,100 @@ def run_b200(args, out):
         line["e2e"] = run_e2e(args, X, y, params, dev, world, rank, n_total, group)
     if world > 1:
         torch.distributed.barrier()
-    del X, y
+    # ---- the other BASELINE.json configs, each with its stock-op comparator (N = 1 only; reporting) ----------
+    if rank == 0 and world == 1 and not args.no_configs:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            line["configs"] = bench_configs.run_all(dev, X=X if args.log2n >= 22 else None)
+        except Exception as exc:
+            line["configs"] = {"error": repr(exc)[:300]}
+    del X, y, e, pi
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_configs:
+        try:
+            line["configs"]["config3_pca_fp32"] = bench_configs.config3(dev, log2n=args.config3_log2n)
+        except Exception as exc:
+            line["configs"]["config3_pca_fp32"] = {"error": repr(exc)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_em_step_bench(args.cpu_log2n, d, 1, 1)
+        line["cpu_baseline"], _, held = cpu_em_step_bench(args.cpu_log2n, d, 1, 1, keep=True)
+        # ---- parity on the CPU leg's own data: the CUDA step against the oracle's outputs ----
+        try:
+            line["parity"] = parity_block(held, dev)
+        except Exception as exc:
+            line["parity"] = {"error": repr(exc)[:300]}
+        # ---- the user-visible call: NumPy in, NumPy out, whole EM loop, against the oracle on the same data ------
+        try:
+            line["e2e_call"] = e2e_call_block(held, dev)
+        except Exception as exc:
+            line["e2e_call"] = {"error": repr(exc)[:300]}
     if rank == 0:
         emit(out, line)
     if world > 1:
         group.close()
         torch.distributed.destroy_process_group()
+
+
+def parity_block(held, dev):
+    """One CUDA E+M step on the host data the cpu_baseline leg used, compared with the oracle's outputs for that step.
+    Tolerances are BASELINE.json's: 1e-9 relative for the FP64 statistics and epsilon, equal iteration count, raw
+    posteriors at SURVEY.md H1's max(1e-9, 4 * 2^-53 / mean pi), identical selection masks."""
+    import numpy as np
+    import torch
+
+    from rlvi_b200 import ops
+
+    X, y, params, ref = held[:4]
+    n, d = X.shape
+    Xd, yd, pd = (torch.from_numpy(a).to(dev) for a in (X, y, params))
+    _, e, _ = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, pd, y=yd, intercept=True, want_losses=False, want_e=True)
+    pi, res = ops.fixed_point(None, e_work=e)
+    mom = ops.weighted_moments(Xd, pi)
+    r = ops.read_result(res)
+    m = {k: v.cpu().numpy() for k, v in ops.split_moments(mom, d).items()}
+    pih = pi.cpu().numpy()
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+    mean_pi = float(ref["pi"].mean())
+    pi_tol = max(1e-9, 4 * 2.0 ** -53 / mean_pi)
+    out = {"n": int(n), "d": int(d), "iters": int(r["iters"]), "iters_ref": int(ref["iters"]),
+           "iters_equal": bool(r["iters"] == ref["iters"]), "eps_rel": abs(r["eps"] - ref["eps"]) / abs(ref["eps"]),
+           "G_rel": rel(m["G"] / m["S0"], ref["G"] / ref["S0"]), "S1_rel": rel(m["S1"] / m["S0"], ref["S1"] / ref["S0"]),
+           "pi_rel": rel(pih, ref["pi"]), "pi_tol": pi_tol, "mean_pi": mean_pi,
+           "pi_normalised_rel": rel(pih / pih.sum(), ref["pi"] / ref["pi"].sum()),
+           "mask_equal": bool(np.array_equal(pih > 0.5 * pih.max(), ref["pi"] > 0.5 * ref["pi"].max())),
+           "oracle": "oracle.rlvi_np.em_step_logistic on the cpu_baseline sample"}
+    out["within_tolerance"] = bool(out["iters_equal"] and out["eps_rel"] <= 1e-9 and out["G_rel"] <= 1e-9 and
+                                   out["S1_rel"] <= 1e-8 and out["pi_rel"] <= pi_tol and out["mask_equal"])
+    return out
+
+
+def e2e_call_block(held, dev):
+    """`rlvi.logistic_regression(X_np, y_np, mstep="mm")` -- the call a user of the reference makes: NumPy in, NumPy
+    out, the whole EM loop (H2D copy once, then iterate on the device) -- timed against the oracle's restatement of
+    the same loop (rlvi.py:92-108 with utils.mm_log_reg) on the same host arrays and all host cores."""
+    import numpy as np
+    import torch
+
+    from rlvi_b200 import ops, rlvi
+
+    X, y, _, _, th_ref, t_cpu = held
+    n, d = X.shape
+    rlvi.logistic_regression(X[:4096], y[:4096], mstep="mm")          # warm-up: handles, scratch
+    torch.cuda.synchronize()
+    l0 = ops.launch_count(dev.index or 0)
+    t0 = time.perf_counter()
+    th = rlvi.logistic_regression(X, y, mstep="mm")
+    t_gpu = time.perf_counter() - t0
+    launches = ops.launch_count(dev.index or 0) - l0
+    return {"call": "rlvi.logistic_regression(X_np, y_np, mstep='mm')", "n": int(n), "d": int(d), "seconds": t_gpu,
+            "samples_per_s": n / t_gpu, "oracle_seconds": t_cpu, "oracle_samples_per_s": n / t_cpu,
+            "speedup_vs_oracle": t_cpu / t_gpu, "theta_rel": float(np.max(np.abs(th - th_ref)) / np.max(np.abs(th_ref))),
+            "h2d_bytes": int(n * (d + 1) * 8), "d2h_bytes": int((d + 1) * 8), "library_launches": int(launches),
+            "note": "X, y copied host->device once (pageable NumPy memory), EM iterations on the device, theta copied "
+                    "back; the oracle is oracle.rlvi_np.logistic_regression_mm on the same arrays"}
 
 
 def m_step_extras(X, y, pi, params, mom, d):

@@ -203,6 +203,28 @@ int rlvi_weighted_moments_centered_f64(rlvi_ctx* ctx, const double* X, const dou
                                        const double* center, int64_t n, int d, int power, int want_gram,
                                        double* out, void* stream);
 
+/* ---- FP32-stored samples (SURVEY.md section 8d "FP32 mode"; BASELINE.json config 3: N = 2^24, d = 512) ---------
+ * X is float32 [n][d] row-major; every per-sample vector (y, weights, losses, e) and every statistic stays FP64.
+ * The Gram contraction runs on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
+ *   RLVI_TF32X3  three TF32 products per term (hi*hi + lo*hi + hi*lo) with short FP32 accumulation chains flushed
+ *                into FP64: the statistics agree with an FP64 evaluation on the same float32 samples to ~1e-6
+ *                (the 1e-5 FP32 tolerance of BASELINE.json's north_star); default;
+ *   RLVI_TF32X1  one TF32 product per term (operands rounded to 11 bits, zero-mean error): 3x fewer tensor-core
+ *                flops, ~1e-3 / sqrt(rows) relative accuracy.
+ * Same output layout as rlvi_weighted_moments_f64.  Replaces utils.py:82-84 (power = 2), rlvi.py:70-71,79-80 and
+ * utils.py:36-38 (power = 1) for float32 inputs.  d <= 512 with d % 4 == 0 and a 16-byte aligned X take the tensor
+ * path; other shapes (d <= 1024) are converted chunk-wise and summed by the FP64 kernels. */
+#define RLVI_TF32X3 0
+#define RLVI_TF32X1 1
+int rlvi_weighted_moments_f32(rlvi_ctx* ctx, const float* X, const double* y, const double* weights, int64_t n,
+                              int d, int power, int want_gram, int precision, double* out, void* stream);
+
+/* rlvi_loss_f64 for float32 samples (all kinds except RLVI_LOSS_GAUSSIAN; d <= 4096): products and sums in FP64
+ * from the converted samples, outputs FP64. */
+int rlvi_loss_f32(rlvi_ctx* ctx, int kind, int intercept, const float* X, const double* y, int64_t n, int d,
+                  const double* params, const double* weights, double* losses_out, double* e_out, double* wsum_out,
+                  void* stream);
+
 /* utils.py:40-41  the MM/gradient step's data term:  out[0] = sum c_i, out[1..d] = X^T c with
  * c_i = w_i (sigmoid(b + x_i.theta) - y_i);  params = [b, theta(d)].  `out` = device double[d+1]. */
 int rlvi_logistic_grad_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,

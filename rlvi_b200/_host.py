@@ -39,5 +39,13 @@ def as_device(a, like=None, dtype=torch.float64):
     return torch.from_numpy(arr).to(dev), True
 
 
+def as_device_x(a, like=None):
+    """`as_device` for a sample matrix: float32 input stays float32 (the FP32-stored mode: rlvi_loss_f32 /
+    rlvi_weighted_moments_f32 on the TF32 tensor cores), everything else becomes float64 as in the reference."""
+    is32 = (isinstance(a, torch.Tensor) and a.dtype == torch.float32) or \
+           (isinstance(a, np.ndarray) and a.dtype == np.float32)
+    return as_device(a, like=like, dtype=torch.float32 if is32 else torch.float64)
+
+
 def to_caller(t, was_numpy):
     return t.cpu().numpy() if was_numpy else t

@@ -19,11 +19,12 @@ SYMBOLS = (
     "rlvi_fixed_point_deep_f32", "rlvi_shift_sum_f64", "rlvi_shift_sum_e_f64", "rlvi_loss_f64", "rlvi_moments_out_doubles",
     "rlvi_weighted_moments_f64", "rlvi_weighted_moments_centered_f64", "rlvi_logistic_grad_f64", "rlvi_wce_fwd_bwd_f32", "rlvi_fn_threshold_f32",
     "rlvi_em_step_logistic_host", "rlvi_dist_window_create", "rlvi_dist_window_open", "rlvi_dist_window_close",
-    "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded",
+    "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded", "rlvi_weighted_moments_f32", "rlvi_loss_f32",
 )
 
 FP_STANDARD, FP_ONLINE, FP_DEEP = 0, 1, 2
 LOSS_LOGISTIC_CE, LOSS_SOFTPLUS, LOSS_SQRES, LOSS_SQDIST, LOSS_PCA, LOSS_GAUSSIAN = range(6)
+TF32X3, TF32X1 = 0, 1
 
 
 class FpResult(C.Structure):
@@ -73,6 +74,8 @@ def load():
         lib.rlvi_moments_out_doubles.argtypes = [i32]
         lib.rlvi_weighted_moments_f64.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp]
         lib.rlvi_weighted_moments_centered_f64.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp]
+        lib.rlvi_weighted_moments_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
+        lib.rlvi_loss_f32.argtypes = [vp, i32, i32, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp]
         lib.rlvi_logistic_grad_f64.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
         lib.rlvi_wce_fwd_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp]
         lib.rlvi_fn_threshold_f32.argtypes = [vp, vp, i64, f32, f32, i32, vp, vp]

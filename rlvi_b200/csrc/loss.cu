@@ -550,6 +550,126 @@ int launch_loss(rlvi_ctx* ctx, const RowMapCfg& cfg, LossParams& p, int grid, si
   return RLVI_ERR_UNSUPPORTED;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// FP32-STORED X (the FP32 mode of SURVEY.md section 8d, config C3): the same losses from float32 samples.
+// The per-sample vectors stay FP64 (l, e, pi, y); products and sums are formed in FP64 from the converted
+// samples, so the only difference to the FP64 path is the storage rounding of X itself.  One warp per row:
+// lane l takes the 16-byte units l, l + 32, ... (coalesced 512-byte requests), theta sits in shared memory.
+// HBM-bound: d*4 (X) + 8 (y) [+ 8 (pi)] in, 8 (l) and/or 8 (e) out per sample.
+// ---------------------------------------------------------------------------------------------
+struct LossF32Params {
+  const float* X;
+  const double* y;
+  const double* params;
+  const double* w;
+  double* losses;
+  double* e_out;
+  double* wsum_out;
+  int64_t n;
+  int d;
+  int kind;
+  int intercept;
+  int vec;                // X 16-byte aligned and d % 4 == 0
+  double* partials;       // [grid][2]
+  unsigned int* ticket;
+};
+
+template <int DOTK>
+__global__ void __launch_bounds__(kLossThreads) loss_f32_kernel(const LossF32Params p) {
+  extern __shared__ double sm[];
+  double* sm_params = sm;                           // [intercept] + d, padded to a multiple of 4
+  double* sm_red = sm + ((p.d + 1 + 3) & ~3) + 4;   // 2 * nwarps
+  const int np = p.d + (p.intercept ? 1 : 0);
+  for (int i = threadIdx.x; i < np; i += blockDim.x) sm_params[i + (p.intercept ? 0 : 1)] = p.params[i];
+  __syncthreads();
+  const double* th = sm_params + 1;                 // theta[0..d), 8-byte aligned
+  const double b0 = p.intercept ? sm_params[0] : 0.0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
+  const int64_t warp_id = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double s_wl = 0.0, s_w = 0.0;
+
+  for (int64_t row = warp_id; row < p.n; row += warps_total) {
+    const float* xr = p.X + row * p.d;
+    double a = 0.0, b = 0.0;
+    if (p.vec) {
+      for (int j0 = 0; j0 < p.d; j0 += 512) {       // up to 4 independent 16-byte loads in flight per lane
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 128 + lane * 4;
+          x[u] = (j < p.d) ? ld_stream_f4(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 128 + lane * 4;
+          if (j < p.d) {
+            const double xv[4] = {double(x[u].x), double(x[u].y), double(x[u].z), double(x[u].w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (DOTK == 2) {
+                const double t = th[j + k] - xv[k];
+                a = fma(t, t, a);
+              } else {
+                a = fma(xv[k], th[j + k], a);
+                if (DOTK == 1) b = fma(xv[k], xv[k], b);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int j = lane; j < p.d; j += 32) {
+        const double xv = double(xr[j]);
+        if (DOTK == 2) {
+          const double t = th[j] - xv;
+          a = fma(t, t, a);
+        } else {
+          a = fma(xv, th[j], a);
+          if (DOTK == 1) b = fma(xv, xv, b);
+        }
+      }
+    }
+    a = warp_sum(a);
+    if (DOTK == 1) b = warp_sum(b);
+    if (lane == 0) {
+      const double loss = finish_loss(p.kind, a, b, b0, (p.kind == RLVI_LOSS_LOGISTIC_CE || p.kind == RLVI_LOSS_SQRES) ? p.y[row] : 0.0);
+      if (p.losses) p.losses[row] = loss;
+      if (p.e_out) p.e_out[row] = exp(-loss);
+      if (p.w) {
+        const double wi = p.w[row];
+        s_wl = fma(wi, loss, s_wl);
+        s_w += wi;
+      }
+    }
+  }
+
+  if (p.w) {   // uniform across the grid
+    double v[2] = {s_wl, s_w};
+    block_sum<2>(v, sm_red);
+    if (threadIdx.x == 0) {
+      p.partials[2 * blockIdx.x] = v[0];
+      p.partials[2 * blockIdx.x + 1] = v[1];
+    }
+    if (last_block_ticket(p.ticket, gridDim.x)) {
+      if (threadIdx.x < 32) {
+        double a0 = 0.0, a1 = 0.0;
+        for (unsigned int j = lane; j < gridDim.x; j += 32) {
+          a0 += p.partials[2 * j];
+          a1 += p.partials[2 * j + 1];
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+          p.wsum_out[0] = a0;
+          p.wsum_out[1] = a1;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const double* X, const double* y, int64_t n,
@@ -706,4 +826,49 @@ extern "C" int rlvi_loss_f64(rlvi_ctx* ctx, int kind, int intercept, const doubl
   if (kind == RLVI_LOSS_PCA) return launch_loss<1>(ctx, cfg, p, grid, smem, st);
   if (kind == RLVI_LOSS_SQDIST) return launch_loss<2>(ctx, cfg, p, grid, smem, st);
   return launch_loss<0>(ctx, cfg, p, grid, smem, st);
+}
+
+extern "C" int rlvi_loss_f32(rlvi_ctx* ctx, int kind, int intercept, const float* X, const double* y, int64_t n, int d,
+                             const double* params, const double* weights, double* losses_out, double* e_out,
+                             double* wsum_out, void* stream) {
+  RLVI_REQUIRE(ctx && X && params, "null pointer");
+  RLVI_REQUIRE(n > 0 && d > 0, "n and d must be positive");
+  RLVI_REQUIRE(kind >= RLVI_LOSS_LOGISTIC_CE && kind <= RLVI_LOSS_PCA, "loss kind not available for FP32 samples");
+  RLVI_REQUIRE(losses_out || e_out || weights, "nothing to compute");
+  RLVI_REQUIRE(!weights || wsum_out, "weights given but wsum_out is null");
+  if (kind == RLVI_LOSS_LOGISTIC_CE || kind == RLVI_LOSS_SQRES) RLVI_REQUIRE(y != nullptr, "this loss needs y");
+  if (d > 4096) {
+    rlvi_set_error("rlvi_loss_f32 supports d <= 4096 (got %d)", d);
+    return RLVI_ERR_UNSUPPORTED;
+  }
+  RlviDeviceGuard guard(ctx->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps_per_block = kLossThreads / 32;
+  int64_t want = (n + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = int64_t(ctx->sm_count) * 8;
+  const int grid = int(want < 1 ? 1 : (want > cap ? cap : want));
+  void* scratch = nullptr;
+  int rc = rlvi_scratch(ctx, 4096 + size_t(grid) * 2 * sizeof(double), &scratch);
+  if (rc != RLVI_OK) return rc;
+  LossF32Params p;
+  p.X = X;
+  p.y = y;
+  p.params = params;
+  p.w = weights;
+  p.losses = losses_out;
+  p.e_out = e_out;
+  p.wsum_out = wsum_out;
+  p.n = n;
+  p.d = d;
+  p.kind = kind;
+  p.intercept = intercept ? 1 : 0;
+  p.vec = (rlvi_aligned16(X) && d % 4 == 0) ? 1 : 0;
+  p.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
+  p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
+  const size_t smem = (size_t((d + 1 + 3) & ~3) + 4 + 2 * warps_per_block) * sizeof(double);
+  if (kind == RLVI_LOSS_PCA) loss_f32_kernel<1><<<grid, kLossThreads, smem, st>>>(p);
+  else if (kind == RLVI_LOSS_SQDIST) loss_f32_kernel<2><<<grid, kLossThreads, smem, st>>>(p);
+  else loss_f32_kernel<0><<<grid, kLossThreads, smem, st>>>(p);
+  RLVI_LAUNCH_CHECK(ctx);
+  return RLVI_OK;
 }

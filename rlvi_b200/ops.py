@@ -13,12 +13,12 @@ import torch
 
 from . import _lib
 from ._lib import (FP_DEEP, FP_ONLINE, FP_STANDARD, LOSS_GAUSSIAN, LOSS_LOGISTIC_CE, LOSS_PCA, LOSS_SOFTPLUS,
-                   LOSS_SQDIST, LOSS_SQRES)
+                   LOSS_SQDIST, LOSS_SQRES, TF32X1, TF32X3)
 
 __all__ = ["FP_STANDARD", "FP_ONLINE", "FP_DEEP", "LOSS_LOGISTIC_CE", "LOSS_SOFTPLUS", "LOSS_SQRES",
            "LOSS_SQDIST", "LOSS_PCA", "LOSS_GAUSSIAN", "fixed_point", "fixed_point_deep", "shift_sum", "shift_sum_e", "loss",
            "weighted_moments", "split_moments", "logistic_grad", "wce_fwd_bwd", "fn_threshold", "read_result",
-           "em_step_logistic_host", "launch_count"]
+           "em_step_logistic_host", "launch_count", "TF32X3", "TF32X1"]
 
 _RESULT_DTYPE = np.dtype([("eps", "<f8"), ("rho", "<f8"), ("sum_pi", "<f8"), ("err", "<f8"), ("iters", "<i4"),
                           ("converged", "<i4")])
@@ -176,12 +176,22 @@ def shift_sum_e(e, scale_t, c, *, pi_out=None, out=None):
     return out
 
 
+def _chk_x(X):
+    """X is float64 (the reference's precision) or float32 (FP32-stored mode: the rlvi_*_f32 entry points).
+    Returns True for float32."""
+    is32 = isinstance(X, torch.Tensor) and X.dtype == torch.float32
+    _chk(X, torch.float32 if is32 else torch.float64, "X")
+    return is32
+
+
 def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=True, want_e=False,
          losses_out=None, e_out=None, wsum_out=None):
-    """rlvi_loss_f64.  Returns (losses | None, e | None, wsum | None)."""
+    """rlvi_loss_f64 (float64 X) / rlvi_loss_f32 (float32 X).  Returns (losses | None, e | None, wsum | None)."""
     dev = _dev(X)
     f64 = torch.float64
-    _chk(X, f64, "X")
+    x32 = _chk_x(X)
+    if x32 and kind == LOSS_GAUSSIAN:
+        raise ValueError("the Gaussian loss has no FP32-stored variant")
     if X.dim() != 2:
         raise ValueError("X must be [n, d]")
     n, d = X.shape
@@ -203,18 +213,22 @@ def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=
     if weights is not None and wsum_out is None:
         wsum_out = torch.empty(2, dtype=f64, device=X.device)
     ctx = _ctx(dev)
-    rc = ctx.lib.rlvi_loss_f64(ctx.handle, int(kind), 1 if intercept else 0, _p(X), _p(y), n, d, _p(params),
-                               _p(weights), _p(losses_out), _p(e_out), _p(wsum_out), _stream(dev))
-    _lib.check(rc, "rlvi_loss_f64")
+    fn = ctx.lib.rlvi_loss_f32 if x32 else ctx.lib.rlvi_loss_f64
+    rc = fn(ctx.handle, int(kind), 1 if intercept else 0, _p(X), _p(y), n, d, _p(params),
+            _p(weights), _p(losses_out), _p(e_out), _p(wsum_out), _stream(dev))
+    _lib.check(rc, "rlvi_loss_f32" if x32 else "rlvi_loss_f64")
     return losses_out, e_out, wsum_out
 
 
-def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, center=None):
-    """rlvi_weighted_moments_f64 (or, with `center`, rlvi_weighted_moments_centered_f64: x_i -> x_i - center).
-    Returns the flat device buffer [S0, Swy, S1(d), Sy(d), G(d*d)]; `split_moments` gives views."""
+def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, center=None, precision=TF32X3):
+    """rlvi_weighted_moments_f64 (or, with `center`, rlvi_weighted_moments_centered_f64: x_i -> x_i - center);
+    float32 X -> rlvi_weighted_moments_f32 (tcgen05 TF32 tensor-core Gram, `precision` = TF32X3 | TF32X1).
+    Returns the flat device buffer [S0, Swy, S1(d), Sy(d), G(d*d)] (FP64); `split_moments` gives views."""
     dev = _dev(X)
     f64 = torch.float64
-    _chk(X, f64, "X")
+    x32 = _chk_x(X)
+    if x32 and center is not None:
+        raise ValueError("the centred statistics have no FP32-stored variant")
     if X.dim() != 2:
         raise ValueError("X must be [n, d]")
     n, d = X.shape
@@ -225,6 +239,11 @@ def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, c
         out = torch.zeros(ctx.lib.rlvi_moments_out_doubles(d), dtype=f64, device=X.device)
     _len(_chk(out, f64, "out"), ctx.lib.rlvi_moments_out_doubles(d), "out")
     _same_device(X, weights, y, out, center)
+    if x32:
+        rc = ctx.lib.rlvi_weighted_moments_f32(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
+                                               1 if want_gram else 0, int(precision), _p(out), _stream(dev))
+        _lib.check(rc, "rlvi_weighted_moments_f32")
+        return out
     if center is None:
         rc = ctx.lib.rlvi_weighted_moments_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, int(power),
                                                1 if want_gram else 0, _p(out), _stream(dev))

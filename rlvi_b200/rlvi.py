@@ -26,7 +26,7 @@ from scipy import optimize as _opt
 
 from . import ops
 from . import utils as _utils
-from ._host import as_device, to_caller
+from ._host import as_device, as_device_x, to_caller
 
 __all__ = ["update_weights", "update_weights_constrained", "mean", "linear_regression", "logistic_regression",
            "pca", "covariance"]
@@ -189,8 +189,8 @@ def logistic_regression(X, y, maxiter=100, tol=1e-2, mstep="sklearn"):
 
 
 def pca(sample, maxiter=100, tol=1e-2, theta_init=None):
-    """rlvi.py:111-125."""
-    X, was_np = as_device(sample)
+    """rlvi.py:111-125.  A float32 `sample` runs in the FP32-stored mode (utils.pca)."""
+    X, was_np = as_device_x(sample)
     n = X.shape[0]
     pi = torch.ones(n, dtype=torch.float64, device=X.device)
     t0 = None if theta_init is None else as_device(theta_init, like=X)[0]

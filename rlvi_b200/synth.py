@@ -1,7 +1,8 @@
 """Seeded synthetic inputs for the parity tests and the benchmark.
 
-Host generators use `np.random.default_rng(seed)`; the device generators (large N) use a
-`torch.Generator` seeded with `seed + rank` per shard.  Distributions follow the reference's own
+Host generators use `np.random.default_rng(seed)`; the device generators (large N) draw every block of 2^20
+global rows from its own `torch.Generator` seeded by (seed, block index), so a row's values depend on its GLOBAL
+index only: 1, 2, 4 or 8 ranks sharding the same N see exactly the same samples.  Distributions follow the reference's own
 generators where one exists (standard-learning/main.py:44-167) generalised to d features.
 """
 from __future__ import annotations
@@ -132,3 +133,75 @@ def logistic_shard_torch(n, d, device, seed, corruption=0.3, chunk=1 << 22, dtyp
         yb = torch.where(flip, 1.0 - yb, yb)
         y[s:s + m] = yb.to(dtype)
     return X, y, theta
+
+
+ROW_BLOCK = 1 << 20      # rows per independently seeded block of the device generators
+
+
+def theta_star_torch(d, device, seed):
+    """theta* ~ N(0, 1/d) of the logistic workload: a function of (d, seed) only, identical on every rank."""
+    import torch
+
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed) * 7919 + 17)
+    return (torch.randn(d, generator=g, dtype=torch.float64) / (d ** 0.5)).to(device)
+
+
+def logistic_rows_torch(row_lo, row_hi, d, device, seed, corruption=0.3, dtype=None):
+    """Rows [row_lo, row_hi) of the GLOBAL synthetic logistic data set (config C2-logistic: X ~ N(0,1),
+    y ~ Bernoulli(sigmoid(X theta*)), then `corruption` of the labels flipped), on `device`.  Block b of ROW_BLOCK
+    rows is drawn from a generator seeded with (seed, b), so the result does not depend on how the rows are sharded.
+    Returns (X [rows, d], y [rows], theta* [d])."""
+    import torch
+
+    dtype = dtype or torch.float64
+    theta = theta_star_torch(d, device, seed)
+    n = row_hi - row_lo
+    X = torch.empty((n, d), device=device, dtype=dtype)
+    y = torch.empty((n,), device=device, dtype=torch.float64)
+    g = torch.Generator(device=device)
+    b0, b1 = row_lo // ROW_BLOCK, (row_hi + ROW_BLOCK - 1) // ROW_BLOCK
+    for b in range(b0, b1):
+        g.manual_seed(int(seed) * 1000003 + b)
+        xb = torch.empty((ROW_BLOCK, d), device=device, dtype=dtype).normal_(generator=g)
+        p = torch.sigmoid(xb.to(torch.float64) @ theta)
+        yb = (torch.rand(ROW_BLOCK, generator=g, device=device, dtype=torch.float64) < p).to(torch.float64)
+        flip = torch.rand(ROW_BLOCK, generator=g, device=device, dtype=torch.float64) < corruption
+        yb = torch.where(flip, 1.0 - yb, yb)
+        lo, hi = max(row_lo, b * ROW_BLOCK), min(row_hi, (b + 1) * ROW_BLOCK)
+        X[lo - row_lo:hi - row_lo] = xb[lo - b * ROW_BLOCK:hi - b * ROW_BLOCK]
+        y[lo - row_lo:hi - row_lo] = yb[lo - b * ROW_BLOCK:hi - b * ROW_BLOCK]
+        del xb, p, yb, flip
+    return X, y, theta
+
+
+def pca_rows_torch(row_lo, row_hi, d, device, seed, eps=0.2, dtype=None):
+    """Rows [row_lo, row_hi) of the GLOBAL config-3 data set: clean rows z v + 0.25 N(0, I)
+    along the fixed unit direction v ~ (1, 2, ..., d); a fraction `eps` of the rows replaced by N(0, I) / sqrt(chi2_1.5 /
+    1.5) (standard-learning/main.py:126-143 generalised to d features; corruption by a per-row coin instead of a block
+    of trailing rows so that every shard sees the same mixture).  Sharding-invariant like `logistic_rows_torch`.
+    Returns (X [rows, d] `dtype` (default float32), v [d] float64)."""
+    import torch
+
+    dtype = dtype or torch.float32
+    v = torch.arange(1, d + 1, dtype=torch.float64, device=device)
+    v = v / v.norm()
+    n = row_hi - row_lo
+    X = torch.empty((n, d), device=device, dtype=dtype)
+    g = torch.Generator(device=device)
+    nu = 1.5
+    b0, b1 = row_lo // ROW_BLOCK, (row_hi + ROW_BLOCK - 1) // ROW_BLOCK
+    for b in range(b0, b1):
+        g.manual_seed(int(seed) * 1000003 + b)
+        xb = torch.empty((ROW_BLOCK, d), device=device, dtype=torch.float32).normal_(generator=g)
+        z = torch.empty((ROW_BLOCK, 1), device=device, dtype=torch.float32).normal_(generator=g)
+        bad = torch.rand((ROW_BLOCK, 1), generator=g, device=device) < eps
+        # chi2_nu / nu from a Gamma(nu / 2, 2 / nu) draw: -log(U) has no closed form for nu = 1.5, so use the
+        # sum-of-squares identity chi2_1.5 ~ Gamma(0.75, 2) via torch's gamma sampler on the host-independent generator
+        u = torch._standard_gamma(torch.full((ROW_BLOCK, 1), nu / 2, device=device), generator=g) * (2.0 / nu)
+        clean = 2.0 * z * v.to(torch.float32) + 0.25 * xb
+        xb = torch.where(bad, xb / torch.sqrt(u.to(torch.float32)), clean)
+        lo, hi = max(row_lo, b * ROW_BLOCK), min(row_hi, (b + 1) * ROW_BLOCK)
+        X[lo - row_lo:hi - row_lo] = xb[lo - b * ROW_BLOCK:hi - b * ROW_BLOCK].to(dtype)
+        del xb, z, bad, u, clean
+    return X, v

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._host import as_device, to_caller
+from ._host import as_device, as_device_x, to_caller
 
 __all__ = ["sigmoid", "cross_entropy", "clf_predict", "mm_log_reg", "sklearn_log_reg", "pca", "covariance"]
 
@@ -147,16 +147,18 @@ def _svd_flip_unit(v):
     return v / torch.linalg.norm(v)
 
 
-def pca(samples, weights, theta=None):
+def pca(samples, weights, theta=None, precision=ops.TF32X3):
     """utils.py:76-89.  theta = top principal direction of the rows pi_i x_i after column-centring
     (what `PCA(n_components=1).fit(diag(pi) @ X)` returns: quirk Q4 -- weights pi, not sqrt(pi)), from
     G = sum pi_i^2 x_i x_i^T and m = sum pi_i x_i / N:  C = (G - N m m^T)/(N-1), top eigenvector, sklearn's
-    sign rule, unit norm.  losses_i = ||x_i||^2 - (x_i . theta)^2 (uncentred)."""
-    X, was_np = as_device(samples)
+    sign rule, unit norm.  losses_i = ||x_i||^2 - (x_i . theta)^2 (uncentred).
+    float32 `samples` stay float32 on the device (FP32-stored mode): the Gram runs on the TF32 tensor cores
+    (`precision`), losses / weights / theta stay FP64."""
+    X, was_np = as_device_x(samples)
     n, d = X.shape
     if theta is None:
         wd, _ = as_device(weights, like=X)
-        mom = ops.weighted_moments(X, wd, power=2)
+        mom = ops.weighted_moments(X, wd, power=2, precision=precision)
         m = ops.split_moments(mom, d)
         mu = m["S1"] / n
         Cm = (m["G"] - n * torch.outer(mu, mu)) / (n - 1)

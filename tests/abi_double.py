@@ -115,6 +115,7 @@ def shift_sum_e(e, scale_t, c, *, pi_out=None, out=None):
 
 def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=True, want_e=False, losses_out=None,
          e_out=None, wsum_out=None):
+    X = X.double()                                        # float32 X = the FP32-stored mode: FP64 arithmetic on it
     d = X.shape[1]
     if kind in (ops.LOSS_LOGISTIC_CE, ops.LOSS_SOFTPLUS, ops.LOSS_SQRES):
         b, theta = (params[0], params[1:]) if intercept else (0.0, params)
@@ -143,7 +144,8 @@ def loss(kind, X, params, *, y=None, intercept=False, weights=None, want_losses=
     return losses_out, e_out, wsum_out
 
 
-def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, center=None):
+def weighted_moments(X, weights, *, y=None, power=1, want_gram=True, out=None, center=None, precision=0):
+    X = X.double()
     n, d = X.shape
     if out is None:
         out = torch.zeros(2 + 2 * d + d * d, dtype=torch.float64)
@@ -215,5 +217,8 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, globals()[name])
     for mod in (rlvi, utils, online):
         monkeypatch.setattr(mod, "as_device", _as_device)
+    for mod in (rlvi, utils):
+        monkeypatch.setattr(mod, "as_device_x", lambda a, like=None: _as_device(
+            a, like, torch.float32 if getattr(a, "dtype", None) in (torch.float32, np.float32, np.dtype("float32")) else torch.float64))
     monkeypatch.setattr(_host, "as_device", _as_device)
     return deep

@@ -202,7 +202,7 @@ def test_standard_signatures():
     assert sig(utils.clf_predict) == [("X", E_), ("theta", E_), ("augment", True)]
     assert sig(utils.mm_log_reg) == [("X", E_), ("y", E_), ("weights", E_)]
     assert sig(utils.sklearn_log_reg)[:4] == [("X", E_), ("y", E_), ("weights", E_), ("reg_coeff", 1e2)]
-    assert sig(utils.pca) == [("samples", E_), ("weights", E_), ("theta", None)]
+    assert sig(utils.pca)[:3] == [("samples", E_), ("weights", E_), ("theta", None)]   # + keyword `precision` (FP32 mode)
     assert sig(utils.covariance) == [("samples", E_), ("weights", E_), ("mean", None)]
 
 

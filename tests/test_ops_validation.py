@@ -191,3 +191,21 @@ def test_first_context_call_loads_the_library_without_deadlock():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "created" in r.stdout or "refused" in r.stdout
+
+
+def test_fp32_mode_calls_reach_the_f32_entry_points(rec):
+    """float32 X selects rlvi_loss_f32 / rlvi_weighted_moments_f32 (per-sample vectors stay float64)."""
+    n, d = 64, 16
+    X = f32(n, d)
+    ops.loss(ops.LOSS_PCA, X, f64(d), want_e=True)
+    ops.weighted_moments(X, f64(n), power=2, precision=ops.TF32X1)
+    names = [c[0] for c in rec.calls]
+    assert names == ["rlvi_loss_f32", "rlvi_weighted_moments_f32"]
+    args = rec.calls[1][1]
+    assert args[4:9] == (n, d, 2, 1, ops.TF32X1)
+    with pytest.raises(ValueError):
+        ops.loss(ops.LOSS_GAUSSIAN, X, f64(1 + d + d * d))
+    with pytest.raises(ValueError):
+        ops.weighted_moments(X, f64(n), center=f64(d))
+    with pytest.raises(TypeError):
+        ops.weighted_moments(X, f32(n))          # weights must be float64
