@@ -55,6 +55,22 @@ def test_moments_f32_tf32x3_matches_oracle(n, d, power, with_y):
         assert abs(m["Swy"] - r["Swy"]) < 1e-9 * abs(r["Swy"]) + 1e-12
 
 
+@pytest.mark.parametrize("scale", [1e-7, 1e-20, 1e-150, 1e40])
+def test_moments_f32_collapse_regime_weights(scale):
+    """the posteriors of a converged fixed point are ~1e-7 and smaller; pi^2 x^2 would leave the FP32 range.
+    The kernel normalises the weights by a power of two and scales the statistics back: same accuracy at any scale."""
+    rng = np.random.default_rng(21)
+    n, d = 30000, 256
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    w = scale * rng.random(n) ** 3
+    y = rng.normal(size=n)
+    for power in (1, 2):
+        m = gpu_moments(X, w, y, power)
+        r = oracle_moments(X, w, y, power)
+        assert rel(m["G"], r["G"]) < TOL32 and rel(m["S1"], r["S1"]) < TOL32 and rel(m["Sy"], r["Sy"]) < TOL32
+        assert abs(m["S0"] - r["S0"]) < 1e-9 * r["S0"]
+
+
 def test_moments_f32_fallback_shapes():
     """d % 4 != 0, d > 512 and an unaligned X take the FP64 route: FP64-level agreement."""
     rng = np.random.default_rng(5)

@@ -4,7 +4,7 @@ golden vectors produced by the unmodified reference (tests/golden/, oracle/make_
 
 Tolerances (BASELINE.json north_star): 1e-9 relative for FP64 statistics and epsilon, 1e-5 for FP32
 posteriors and losses, identical selection masks.  Raw posteriors in the collapse regime
-are compared at max(1e-9, 8 ulp(1) / mean pi).
+are compared at SURVEY.md H1's max(1e-9, 4 * 2^-53 / mean pi).
 """
 import numpy as np
 import pytest
@@ -39,7 +39,7 @@ def relmax(a, b):
 
 
 def pi_tol(ref_pi):
-    return max(F64_TOL, 8 * 2.0 ** -52 / max(float(np.mean(ref_pi)), 1e-300))
+    return max(F64_TOL, 4 * 2.0 ** -53 / max(float(np.mean(ref_pi)), 1e-300))
 
 
 def test_concurrent_streams_use_separate_contexts(dev):

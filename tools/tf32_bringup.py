@@ -27,11 +27,11 @@ def rel(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
 
-def case(n, d, power, with_y, precision, seed=0):
+def case(n, d, power, with_y, precision, seed=0, wscale=1.0):
     rng = np.random.default_rng(seed)
     X = rng.normal(size=(n, d)).astype(np.float32)
     X[:, 0] += 3.0
-    w = rng.random(n) ** 4
+    w = wscale * rng.random(n) ** 4
     y = rng.normal(size=n) if with_y else None
     dev = torch.device("cuda", 0)
     Xd = torch.from_numpy(X).to(dev)
@@ -59,6 +59,8 @@ def main():
     for c in cases:
         for prec in (ops.TF32X3, ops.TF32X1):
             print(json.dumps(case(*c, prec)), flush=True)
+    print(json.dumps(dict(case(20000, 512, 2, True, ops.TF32X3, wscale=1e-20), wscale=1e-20)), flush=True)
+    print(json.dumps(dict(case(20000, 256, 1, True, ops.TF32X3, wscale=1e-150), wscale=1e-150)), flush=True)
     # loss_f32 vs numpy
     rng = np.random.default_rng(1)
     n, d = 5000, 512
