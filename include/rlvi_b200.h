@@ -230,6 +230,26 @@ int rlvi_loss_f32(rlvi_ctx* ctx, int kind, int intercept, const float* X, const 
 int rlvi_logistic_grad_f64(rlvi_ctx* ctx, const double* X, const double* y, const double* weights,
                            int64_t n, int d, const double* params, double* out, void* stream);
 
+/* utils.py:7-16  overflow-free logistic function of an N-vector: out_i = 1 / (1 + exp(-x_i)). */
+int rlvi_sigmoid_f64(rlvi_ctx* ctx, const double* x, int64_t n, double* out, void* stream);
+
+/* online-learning/main.py:84-85  cross_entropy: out_i = -t_i l_i - (1 - t_i) l_i (== -l_i up to rounding: quirk Q11). */
+int rlvi_online_ce_f64(rlvi_ctx* ctx, const double* log_proba, const double* targets, int64_t n, double* out, void* stream);
+
+/* Curvature weights of the L2-regularised logistic objective utils.py:61-73 hands to liblinear
+ * (1/2 ||theta||^2 + C sum_i pi_i logloss_i): out_i = weights_i e_i (1 - e_i), where e_i = exp(-cross_entropy_i) is
+ * what rlvi_loss_f64(LOGISTIC_CE, e_out) leaves behind (= sigmoid or 1 - sigmoid for a 0/1 label, either way
+ * e (1 - e) = s (1 - s)).  rlvi_weighted_moments_f64 with these weights is the exact Hessian of the data term: the
+ * Newton / IRLS M-step of the drop-in's sklearn_log_reg. */
+int rlvi_irls_weights_f64(rlvi_ctx* ctx, const double* e, const double* weights, int64_t n, double* out, void* stream);
+
+/* standard-learning/rrm.py:12-33 (= online-learning/main.py:61-81 update_weights_rrm), the competitor weight rule on
+ * the same reduction skeleton:  out_sum[0] = sum_i max(exp(-l_i * inv_alpha), cutoff)
+ * (one evaluation of the objective SciPy's Brent minimises, rrm.py:17-21); if w_out != NULL also
+ * w_out_i = exp(-l_i * inv_alpha) * norm (the final weights, rrm.py:32). */
+int rlvi_rrm_sum_f64(rlvi_ctx* ctx, const double* losses, int64_t n, double inv_alpha, double cutoff, double norm,
+                     double* w_out, double* out_sum, void* stream);
+
 /* ---- deep path (FP32) ------------------------------------------------------------------------- */
 /* methods/train_rlvi.py:89-94 fused with its autograd backward (line 96):
  *   loss_i = CE(logits_i, label_i);  residuals[indexes_i] = loss_i (detached: quirk Q8);

@@ -288,6 +288,44 @@ def covariance(sample, eps, maxiter=100, tol=1e-2):
 
 
 # --------------------------------------------------------------------------------------------------
+# Competitor weight rule on the same path (standard-learning/rrm.py)
+# --------------------------------------------------------------------------------------------------
+def rrm_update_weights(losses, eps):
+    """standard-learning/rrm.py:12-33 (= online-learning/main.py:61-81): Robust Risk Minimization weights."""
+    res = np.copy(losses)
+    t = -np.log((1 - eps) * res.shape[0])
+    cutoff = 1e-16
+
+    def objective(xi):
+        phi = np.exp(-res * np.exp(-xi))
+        phi[phi < cutoff] = cutoff
+        return np.exp(xi) * (np.log(np.sum(phi)) + t)
+
+    alpha = np.exp(_opt.minimize_scalar(objective)["x"])
+    phi = np.exp(-res / alpha)
+    phi[phi < cutoff] = cutoff
+    beta_over_alpha = np.log(np.sum(phi)) - 1
+    return np.exp(-res / alpha) * np.exp(-beta_over_alpha - 1)
+
+
+def rrm_linear_regression(X, y, eps, maxiter=100, tol=1e-3):
+    """standard-learning/rrm.py:55-75 with `diag(sqrt(w)) @ A` written as a row scaling."""
+    def fit(w):
+        sw = np.sqrt(w)
+        theta = _lstsq(sw[:, None] * X, sw * y)[0]
+        return theta, (y - X @ theta) ** 2
+
+    theta, losses = fit(np.ones(X.shape[0]) / X.shape[0])
+    for _ in range(maxiter):
+        w = rrm_update_weights(losses, eps)
+        prev = theta.copy()
+        theta, losses = fit(w)
+        if _rel_change(theta, prev) <= tol:
+            break
+    return theta
+
+
+# --------------------------------------------------------------------------------------------------
 # The benchmark's unit of work: one E+M step of the logistic model (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------------------
 def em_step_logistic(X, y, theta, tol=1e-3, maxiter=100):

@@ -575,6 +575,18 @@ struct LossF32Params {
   unsigned int* ticket;
 };
 
+// float -> double on the integer pipe: F2F.F64.F32 issues at ~4 lanes / clk / SM on B200 (measured: the conversion, not
+// HBM, bounded the first version of this kernel at 3.9 TB/s), a shift / add / select sequence at 64.  Exact for normal
+// numbers and zero; denormals (|x| < 2^-126) flush to zero; Inf / NaN take the slow path.
+__device__ __forceinline__ double f32_to_f64(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t a = u & 0x7FFFFFFFu;
+  if (a >= 0x7F800000u) return double(f);
+  const uint32_t hi = (a < 0x00800000u) ? 0u : ((a >> 3) + 0x38000000u);   // exponent bias 127 -> 1023
+  const uint32_t lo = (a < 0x00800000u) ? 0u : (u << 29);
+  return __hiloint2double(int(hi | (u & 0x80000000u)), int(lo));
+}
+
 template <int DOTK>
 __global__ void __launch_bounds__(kLossThreads) loss_f32_kernel(const LossF32Params p) {
   extern __shared__ double sm[];
@@ -605,7 +617,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_f32_kernel(const LossF32Par
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + u * 128 + lane * 4;
           if (j < p.d) {
-            const double xv[4] = {double(x[u].x), double(x[u].y), double(x[u].z), double(x[u].w)};
+            const double xv[4] = {f32_to_f64(x[u].x), f32_to_f64(x[u].y), f32_to_f64(x[u].z), f32_to_f64(x[u].w)};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (DOTK == 2) {

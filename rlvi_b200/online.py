@@ -31,7 +31,7 @@ def update_weights_rlvi(losses, tol=1e-3, maxiter=100, *, init_weight=None, retu
 
 def cross_entropy(log_proba, targets):
     """main.py:84-85 -- -t log_proba - (1-t) log_proba (== -log_proba whatever the label, quirk Q11);
-    the same two-term expression, evaluated on the device."""
+    the same two-term expression, one kernel (rlvi_online_ce_f64)."""
     lp, was_np = as_device(log_proba)
     t, _ = as_device(targets, like=lp)
-    return to_caller(-t * lp - (1 - t) * lp, was_np)
+    return to_caller(ops.online_ce(lp.contiguous(), t.contiguous()).view(lp.shape), was_np)

@@ -18,7 +18,7 @@ from ._lib import (FP_DEEP, FP_ONLINE, FP_STANDARD, LOSS_GAUSSIAN, LOSS_LOGISTIC
 __all__ = ["FP_STANDARD", "FP_ONLINE", "FP_DEEP", "LOSS_LOGISTIC_CE", "LOSS_SOFTPLUS", "LOSS_SQRES",
            "LOSS_SQDIST", "LOSS_PCA", "LOSS_GAUSSIAN", "fixed_point", "fixed_point_deep", "shift_sum", "shift_sum_e", "loss",
            "weighted_moments", "split_moments", "logistic_grad", "wce_fwd_bwd", "fn_threshold", "read_result",
-           "em_step_logistic_host", "launch_count", "TF32X3", "TF32X1"]
+           "em_step_logistic_host", "launch_count", "TF32X3", "TF32X1", "sigmoid", "online_ce", "irls_weights", "rrm_sum"]
 
 _RESULT_DTYPE = np.dtype([("eps", "<f8"), ("rho", "<f8"), ("sum_pi", "<f8"), ("err", "<f8"), ("iters", "<i4"),
                           ("converged", "<i4")])
@@ -282,6 +282,71 @@ def logistic_grad(X, y, weights, params, *, out=None):
     rc = ctx.lib.rlvi_logistic_grad_f64(ctx.handle, _p(X), _p(y), _p(weights), n, d, _p(params), _p(out),
                                         _stream(dev))
     _lib.check(rc, "rlvi_logistic_grad_f64")
+    return out
+
+
+def sigmoid(x, *, out=None):
+    """rlvi_sigmoid_f64: utils.py:7-16 on an N-vector (any shape, flattened)."""
+    dev = _dev(x)
+    _chk(x, torch.float64, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    _len(_chk(out, torch.float64, "out"), x.numel(), "out")
+    _same_device(x, out)
+    if x.numel() == 0:
+        return out
+    ctx = _ctx(dev)
+    _lib.check(ctx.lib.rlvi_sigmoid_f64(ctx.handle, _p(x), x.numel(), _p(out), _stream(dev)), "rlvi_sigmoid_f64")
+    return out
+
+
+def online_ce(log_proba, targets, *, out=None):
+    """rlvi_online_ce_f64: -t l - (1 - t) l (online-learning/main.py:84-85)."""
+    dev = _dev(log_proba)
+    _chk(log_proba, torch.float64, "log_proba")
+    n = log_proba.numel()
+    _len(_chk(targets, torch.float64, "targets"), n, "targets")
+    if out is None:
+        out = torch.empty_like(log_proba)
+    _len(_chk(out, torch.float64, "out"), n, "out")
+    _same_device(log_proba, targets, out)
+    if n == 0:
+        return out
+    ctx = _ctx(dev)
+    _lib.check(ctx.lib.rlvi_online_ce_f64(ctx.handle, _p(log_proba), _p(targets), n, _p(out), _stream(dev)),
+               "rlvi_online_ce_f64")
+    return out
+
+
+def irls_weights(e, weights, *, out=None):
+    """rlvi_irls_weights_f64: out_i = weights_i e_i (1 - e_i)."""
+    dev = _dev(e)
+    _chk(e, torch.float64, "e")
+    n = e.numel()
+    _len(_chk(weights, torch.float64, "weights"), n, "weights")
+    if out is None:
+        out = torch.empty_like(e)
+    _len(_chk(out, torch.float64, "out"), n, "out")
+    _same_device(e, weights, out)
+    ctx = _ctx(dev)
+    _lib.check(ctx.lib.rlvi_irls_weights_f64(ctx.handle, _p(e), _p(weights), n, _p(out), _stream(dev)),
+               "rlvi_irls_weights_f64")
+    return out
+
+
+def rrm_sum(losses, inv_alpha, cutoff=1e-16, *, norm=0.0, w_out=None, out=None):
+    """rlvi_rrm_sum_f64: out[0] = sum_i max(exp(-l_i inv_alpha), cutoff); w_out_i = exp(-l_i inv_alpha) norm."""
+    dev = _dev(losses)
+    _chk(losses, torch.float64, "losses")
+    _len(_chk(w_out, torch.float64, "w_out"), losses.numel(), "w_out")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=losses.device)
+    _len(_chk(out, torch.float64, "out"), 1, "out")
+    _same_device(losses, w_out, out)
+    ctx = _ctx(dev)
+    rc = ctx.lib.rlvi_rrm_sum_f64(ctx.handle, _p(losses), losses.numel(), float(inv_alpha), float(cutoff), float(norm),
+                                  _p(w_out), _p(out), _stream(dev))
+    _lib.check(rc, "rlvi_rrm_sum_f64")
     return out
 
 

@@ -76,8 +76,30 @@ def update_weights_constrained(losses, n_eff, tol=1e-3, maxiter=100):
 # helpers shared by the outer loops
 # --------------------------------------------------------------------------------------------------
 def _rel_change(new, old):
-    """||new - old|| / ||old|| on the host (d-sized)."""
-    return float(torch.linalg.norm(new - old) / torch.linalg.norm(old))
+    """||new - old|| / ||old|| as a DEVICE scalar (d-sized work)."""
+    return torch.linalg.norm(new - old) / torch.linalg.norm(old)
+
+
+def _em_loop(theta, em_step, maxiter, tol, block):
+    """The outer loops of rlvi.py:52-64,75-87,98-107,115-123: `theta <- em_step(theta)` until the relative change is
+    <= tol.  The stop test is evaluated on the device; the host reads `block` of them back at once and returns the
+    FIRST iterate that met it (small problems are sync-bound: a few iterations are issued ahead and the surplus is
+    discarded; large ones use block = 1), so the result is the reference's."""
+    it = 0
+    while it < maxiter:
+        k = min(block, maxiter - it)
+        thetas, rels = [], []
+        for _ in range(k):
+            prev = theta
+            theta = em_step(prev)
+            thetas.append(theta)
+            rels.append(_rel_change(theta, prev))
+        host = torch.stack(rels).cpu()                           # one read-back per block
+        for j in range(k):
+            if float(host[j]) <= tol:
+                return thetas[j]
+        it += k
+    return theta
 
 
 def _estep_scaled(r2, wsum, e_work, pi):
@@ -109,12 +131,14 @@ def mean(sample, maxiter=100, tol=1e-3):
         return theta, wsum
 
     theta, wsum = mstep()
-    for _ in range(maxiter):
+
+    def em_step(_prev):
+        nonlocal wsum
         _estep_scaled(r2, wsum, e_work, pi)                      # rlvi.py:54
-        prev = theta
-        theta, wsum = mstep()
-        if _rel_change(theta, prev) <= tol:                      # rlvi.py:62-64
-            break
+        th, wsum = mstep()
+        return th
+
+    theta = _em_loop(theta, em_step, maxiter, tol, _utils._spec_block(n, d))    # rlvi.py:62-64
     return to_caller(theta, was_np)
 
 
@@ -159,12 +183,14 @@ def linear_regression(X, y, maxiter=100, tol=1e-3):
         return theta, wsum
 
     theta, wsum = mstep()
-    for _ in range(maxiter):
+
+    def em_step(_prev):
+        nonlocal wsum
         _estep_scaled(r2, wsum, e_work, pi)                      # rlvi.py:77
-        prev = theta
-        theta, wsum = mstep()
-        if _rel_change(theta, prev) <= tol:                      # rlvi.py:85-87
-            break
+        th, wsum = mstep()
+        return th
+
+    theta = _em_loop(theta, em_step, maxiter, tol, _utils._spec_block(n, d))    # rlvi.py:85-87
     return to_caller(theta, was_np)
 
 
@@ -174,7 +200,12 @@ def logistic_regression(X, y, maxiter=100, tol=1e-2, mstep="sklearn"):
     reference keeps commented at lines 95/102: utils.mm_log_reg with the true cross-entropy)."""
     Xd, was_np = as_device(X)
     yd, _ = as_device(y, like=Xd)
-    fit = _utils.sklearn_log_reg if mstep == "sklearn" else _utils.mm_log_reg
+    if mstep == "sklearn":        # warm start from the previous EM iterate: same (unique) minimiser, fewer Newton steps
+        def fit(X_, y_, w_, th0=None):
+            return _utils.sklearn_log_reg(X_, y_, w_, theta0=th0)
+    else:
+        def fit(X_, y_, w_, th0=None):
+            return _utils.mm_log_reg(X_, y_, w_)
     n = Xd.shape[0]
     pi = torch.ones(n, dtype=torch.float64, device=Xd.device)
     theta, losses = fit(Xd, yd, pi)
@@ -182,8 +213,8 @@ def logistic_regression(X, y, maxiter=100, tol=1e-2, mstep="sklearn"):
     for _ in range(maxiter):
         ops.fixed_point(losses, e_work=e_work, out=pi, variant=ops.FP_STANDARD)   # rlvi.py:100
         prev = theta
-        theta, losses = fit(Xd, yd, pi)
-        if _rel_change(theta, prev) <= tol:                      # rlvi.py:105-107
+        theta, losses = fit(Xd, yd, pi, prev)
+        if float(_rel_change(theta, prev)) <= tol:               # rlvi.py:105-107
             break
     return to_caller(theta, was_np)
 
@@ -196,12 +227,14 @@ def pca(sample, maxiter=100, tol=1e-2, theta_init=None):
     t0 = None if theta_init is None else as_device(theta_init, like=X)[0]
     theta, losses = _utils.pca(X, pi, t0)
     e_work = torch.empty_like(pi)
-    for _ in range(maxiter):
+
+    def em_step(_prev):
+        nonlocal losses
         ops.fixed_point(losses, e_work=e_work, out=pi, variant=ops.FP_STANDARD)   # rlvi.py:117
-        prev = theta
-        theta, losses = _utils.pca(X, pi)
-        if _rel_change(theta, prev) <= tol:                      # rlvi.py:121-123
-            break
+        th, losses = _utils.pca(X, pi)
+        return th
+
+    theta = _em_loop(theta, em_step, maxiter, tol, _utils._spec_block(n, X.shape[1]))   # rlvi.py:121-123
     return to_caller(theta, was_np)
 
 

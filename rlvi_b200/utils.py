@@ -26,17 +26,15 @@ __all__ = ["sigmoid", "cross_entropy", "clf_predict", "mm_log_reg", "sklearn_log
 
 
 def sigmoid(x):
-    """utils.py:7-16 -- overflow-free logistic function.  A d-sized / scalar helper in the reference's
-    callers; evaluated with torch on whichever device holds `x` (the N-sized sigmoid of the M-step lives
-    inside rlvi_logistic_grad_f64)."""
-    if isinstance(x, torch.Tensor):
-        z = torch.exp(-torch.abs(x))
-        return torch.where(x >= 0, torch.ones_like(z), z) / (1 + z)
-    t, was_np = as_device(np.atleast_1d(x))
-    z = torch.exp(-torch.abs(t))
-    r = torch.where(t >= 0, torch.ones_like(z), z) / (1 + z)
-    r = r.cpu().numpy()
-    return r.reshape(np.shape(x)) if np.ndim(x) else float(r[0])
+    """utils.py:7-16 -- overflow-free logistic function, any shape: one CUDA kernel (rlvi_sigmoid_f64) whatever the size
+    (the N-sized sigmoid of the M-step itself lives inside rlvi_logistic_grad_f64)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        t = x.to(torch.float64).contiguous()
+        return ops.sigmoid(t).view(x.shape)
+    scalar = np.ndim(x) == 0
+    t, _ = as_device(np.atleast_1d(np.asarray(x, dtype=np.float64)))
+    r = ops.sigmoid(t).cpu().numpy().reshape(np.shape(np.atleast_1d(x)))
+    return float(r[0]) if scalar else r.reshape(np.shape(x))
 
 
 def cross_entropy(X, theta, y):
@@ -73,14 +71,22 @@ def _augmented_gram(X, y, weights, mom=None):
     return A
 
 
+def _spec_block(n, d):
+    """How many iterations of a host-tested loop to issue before reading the stop tests back: small problems are
+    launch / sync bound (run a few iterations ahead, discard the surplus), large ones are not (test every one)."""
+    return 1 if n * d >= (1 << 22) else 4
+
+
 def mm_log_reg(X, y, weights):
     """utils.py:32-58 -- MM logistic regression: Q = 1/4 [1,X]^T Pi [1,X] once (one statistics pass),
     then theta <- theta - Q^-1 [1,X]^T (pi * (sigmoid - y)) (one gradient pass each) until
-    ||delta theta|| <= 1e-2; returns (theta [d+1] intercept first, cross-entropy losses)."""
+    ||delta theta|| <= 1e-2; returns (theta [d+1] intercept first, cross-entropy losses).
+    The stop test is evaluated on the device; the host reads the results back once per `_spec_block` steps and
+    returns the FIRST iterate that met it, so the trajectory and the result are the reference's."""
     Xd, was_np = as_device(X)
     yd, _ = as_device(y, like=Xd)
     wd, _ = as_device(weights, like=Xd)
-    d = Xd.shape[1]
+    n, d = Xd.shape
     Q_inv = torch.linalg.inv(0.25 * _augmented_gram(Xd, yd, wd))         # utils.py:36-38
     theta0 = torch.zeros(d + 1, dtype=torch.float64, device=Xd.device)   # utils.py:35
     g = torch.empty(d + 1, dtype=torch.float64, device=Xd.device)
@@ -89,29 +95,46 @@ def mm_log_reg(X, y, weights):
         ops.logistic_grad(Xd, yd, wd, theta, out=g)
         return theta - Q_inv @ g
 
+    block = _spec_block(n, d)
     theta1 = step(theta0)
     n_grad = 1
-    while float(torch.linalg.norm(theta1 - theta0)) > 1e-2:              # utils.py:47
-        theta0 = theta1
-        theta1 = step(theta0)
-        n_grad += 1
+    done = False
+    while not done:
+        thetas, norms = [theta1], [torch.linalg.norm(theta1 - theta0)]   # utils.py:47
+        for _ in range(block - 1):
+            thetas.append(step(thetas[-1]))
+            norms.append(torch.linalg.norm(thetas[-1] - thetas[-2]))
+        host = torch.stack(norms).cpu()                                   # one read-back per block
+        for j in range(block):
+            if not (float(host[j]) > 1e-2):                               # while-condition false: this iterate is returned
+                theta1, done = thetas[j], True
+                n_grad += j
+                break
+        if not done:
+            theta0 = thetas[-1]
+            theta1 = step(theta0)
+            n_grad += block
     mm_log_reg.last_n_grad = n_grad
     losses, _, _ = ops.loss(ops.LOSS_LOGISTIC_CE, Xd, theta1, y=yd, intercept=True)   # utils.py:56
     return to_caller(theta1, was_np), to_caller(losses, was_np)
 
 
-def sklearn_log_reg(X, y, weights, reg_coeff=1e2, gtol=1e-8, max_passes=500):
+def sklearn_log_reg(X, y, weights, reg_coeff=1e2, xtol=1e-9, max_newton=60, theta0=None):
     """utils.py:61-73.  Reproduces the function's observable behaviour:
       * `weights` is normalised IN PLACE by its maximum (line 66, quirk Q3);
       * theta = [intercept, coef] minimises liblinear's objective for `LogisticRegression(C=reg_coeff,
-        solver="liblinear")` with sample weights:  1/2 ||[b, w]||^2 + C sum_i pi_i logloss_i
+        solver="liblinear")` with sample weights:  F = 1/2 ||[b, w]||^2 + C sum_i pi_i logloss_i
         (liblinear regularises the intercept too: intercept_scaling = 1);
       * losses = -log P(class 0 | x) = softplus(b + x.w) for every row whatever its label (lines 62-64).
-    liblinear itself (third-party C++) is not re-implemented: the same convex
-    problem is solved on the device by majorise-minimise steps with the fixed curvature bound
-    I + C/4 [1,X]^T Pi [1,X] (one statistics pass, then one gradient pass per step) until the gradient
-    norm has dropped by `gtol`, which is tighter than liblinear's own stopping rule (tol = 1e-4), so the
-    two agree to liblinear's accuracy."""
+    liblinear itself (third-party C++) is not re-implemented: the same strictly convex
+    problem is solved on the device by damped NEWTON steps (liblinear's own method is a trust-region Newton).  One
+    iteration = three passes over X: the cross-entropy pass (objective value + exp(-loss) for the curvature),
+    the gradient pass (rlvi_logistic_grad_f64) and the statistics pass with the IRLS weights pi s (1 - s)
+    (rlvi_irls_weights_f64 -> rlvi_weighted_moments_f64 = the exact Hessian).  Armijo back-tracking on F makes it
+    globally convergent (nearly separable data, C = 100); it stops when a full Newton step no longer moves theta
+    (||step|| <= xtol (1 + ||theta||): quadratic convergence puts the remaining error at ~xtol^2), far inside
+    liblinear's own tolerance (1e-4).  `theta0` warm-starts the solve (rlvi.logistic_regression passes the previous EM
+    iterate); the minimiser is unique, so the result does not depend on it.  Raises if `max_newton` is exhausted."""
     Xd, was_np = as_device(X)
     yd, _ = as_device(y, like=Xd)
     if isinstance(weights, np.ndarray):
@@ -120,22 +143,59 @@ def sklearn_log_reg(X, y, weights, reg_coeff=1e2, gtol=1e-8, max_passes=500):
     else:
         wd, _ = as_device(weights, like=Xd)
         wd /= wd.max()
-    d = Xd.shape[1]
-    eye = torch.eye(d + 1, dtype=torch.float64, device=Xd.device)
-    H = eye + (0.25 * reg_coeff) * _augmented_gram(Xd, yd, wd)
-    H_inv = torch.linalg.inv(H)
-    theta = torch.zeros(d + 1, dtype=torch.float64, device=Xd.device)
-    g = torch.empty(d + 1, dtype=torch.float64, device=Xd.device)
-    g0 = None
-    for _ in range(max_passes):
+    n, d = Xd.shape
+    dev = Xd.device
+    C = float(reg_coeff)
+    eye = torch.eye(d + 1, dtype=torch.float64, device=dev)
+    theta = torch.zeros(d + 1, dtype=torch.float64, device=dev) if theta0 is None else as_device(theta0, like=Xd)[0].clone()
+    e = torch.empty(n, dtype=torch.float64, device=dev)
+    h = torch.empty(n, dtype=torch.float64, device=dev)
+    g = torch.empty(d + 1, dtype=torch.float64, device=dev)
+    ws = torch.empty(2, dtype=torch.float64, device=dev)
+    mom = None
+    passes = 0
+
+    def objective(th):              # F(th); leaves e_i = exp(-logloss_i(th)) behind
+        nonlocal passes
+        ops.loss(ops.LOSS_LOGISTIC_CE, Xd, th, y=yd, intercept=True, weights=wd, want_losses=False, e_out=e, wsum_out=ws)
+        passes += 1
+        return float(0.5 * (th @ th) + C * ws[0])
+
+    F = objective(theta)
+    converged = False
+    for _ in range(max_newton):
         ops.logistic_grad(Xd, yd, wd, theta, out=g)
-        grad = theta + reg_coeff * g
-        gn = float(torch.linalg.norm(grad))
-        if g0 is None:
-            g0 = gn
-        if gn <= gtol * max(g0, 1e-300):
+        grad = theta + C * g
+        ops.irls_weights(e, wd, out=h)
+        mom = ops.weighted_moments(Xd, h, out=mom)
+        passes += 2
+        m = ops.split_moments(mom, d)
+        A = torch.empty((d + 1, d + 1), dtype=torch.float64, device=dev)
+        A[0, 0] = m["S0"]
+        A[0, 1:] = m["S1"]
+        A[1:, 0] = m["S1"]
+        A[1:, 1:] = m["G"]
+        step = torch.linalg.solve(eye + C * A, grad)
+        slope = float(grad @ step)
+        small = float(torch.linalg.norm(step)) <= xtol * (1.0 + float(torch.linalg.norm(theta)))
+        t = 1.0
+        while True:
+            cand = theta - t * step
+            Fc = objective(cand)
+            if Fc <= F - 1e-4 * t * slope:              # Armijo
+                break
+            if small and Fc <= F + 1e-12 * abs(F):      # at the rounding floor of F: accept the (tiny) full step
+                break
+            if t < 1e-8:
+                break
+            t *= 0.5
+        theta, F = cand, Fc
+        if small and t == 1.0:
+            converged = True
             break
-        theta = theta - H_inv @ grad
+    sklearn_log_reg.last_passes = passes
+    if not converged and np.isfinite(F):
+        raise RuntimeError(f"sklearn_log_reg: Newton iteration did not converge in {max_newton} steps")
     losses, _, _ = ops.loss(ops.LOSS_SOFTPLUS, Xd, theta, intercept=True)   # utils.py:70-71
     return to_caller(theta, was_np), to_caller(losses, was_np)
 

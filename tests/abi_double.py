@@ -167,6 +167,31 @@ def logistic_grad(X, y, weights, params, *, out=None):
     return g if out is None else out.copy_(g)
 
 
+def sigmoid(x, *, out=None):
+    z = torch.exp(-torch.abs(x))
+    r = torch.where(x >= 0, torch.ones_like(z), z) / (1 + z)
+    return r if out is None else out.copy_(r)
+
+
+def online_ce(log_proba, targets, *, out=None):
+    r = -targets * log_proba - (1 - targets) * log_proba
+    return r if out is None else out.copy_(r)
+
+
+def irls_weights(e, weights, *, out=None):
+    r = weights * e * (1 - e)
+    return r if out is None else out.copy_(r)
+
+
+def rrm_sum(losses, inv_alpha, cutoff=1e-16, *, norm=0.0, w_out=None, out=None):
+    phi = torch.exp(-losses * inv_alpha)
+    if w_out is not None:
+        w_out.copy_(phi * norm)
+    out = torch.empty(1, dtype=torch.float64) if out is None else out
+    out[0] = torch.clamp(phi, min=cutoff).sum()
+    return out
+
+
 def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=True, want_per_sample=False,
                 want_correct=False):
     b = logits.shape[0]
@@ -211,11 +236,11 @@ def _as_device(a, like=None, dtype=torch.float64):
 
 def install(monkeypatch):
     """Swap the ops entry points and the host<->device glue of the drop-in modules for the doubles above."""
-    from rlvi_b200 import deep, online, rlvi, utils
+    from rlvi_b200 import deep, online, rlvi, rrm, utils
     for name in ("fixed_point", "fixed_point_deep", "shift_sum", "shift_sum_e", "loss", "weighted_moments",
-                 "logistic_grad", "wce_fwd_bwd", "fn_threshold"):
+                 "logistic_grad", "wce_fwd_bwd", "fn_threshold", "sigmoid", "online_ce", "irls_weights", "rrm_sum"):
         monkeypatch.setattr(ops, name, globals()[name])
-    for mod in (rlvi, utils, online):
+    for mod in (rlvi, utils, online, rrm):
         monkeypatch.setattr(mod, "as_device", _as_device)
     for mod in (rlvi, utils):
         monkeypatch.setattr(mod, "as_device_x", lambda a, like=None: _as_device(
