@@ -62,11 +62,15 @@ __global__ void __launch_bounds__(kWceThreads) wce_kernel(const WceParams p) {
     const float logs = logf(s);
     const int64_t label = p.labels[row];
     const int64_t idx = p.indexes ? p.indexes[row] : row;
-    const float xl = __ldg(x + label);
+    // A label outside [0, C) or an index outside [0, n_train) raises IndexError / a device assert in the reference.
+    // An asynchronous kernel cannot raise: it never reads or writes out of bounds and POISONS the row instead -- NaN
+    // loss, NaN gradient row, NaN batch loss -- so the error is loud at the first host read of the loss.
+    const bool valid = label >= 0 && label < C && idx >= 0 && idx < p.n_train;
+    const float xl = valid ? __ldg(x + label) : __int_as_float(0x7fc00000);
     const float loss = -((xl - m) - logs);                 // -log_softmax[label]
-    const float w = (idx >= 0 && idx < p.n_train) ? p.weights[idx] : 0.f;
+    const float w = valid ? p.weights[idx] : __int_as_float(0x7fc00000);
     if (lane == 0) {
-      if (idx >= 0 && idx < p.n_train) p.residuals[idx] = loss;   // line 90, detached (quirk Q8)
+      if (valid) p.residuals[idx] = loss;                          // line 90, detached (quirk Q8)
       if (p.per_sample) p.per_sample[row] = loss;
       wl_sum += double(loss * w);                                  // line 93: loss * batch_weights in FP32
     }

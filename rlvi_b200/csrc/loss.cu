@@ -587,16 +587,27 @@ __device__ __forceinline__ double f32_to_f64(float f) {
   return __hiloint2double(int(hi | (u & 0x80000000u)), int(lo));
 }
 
+// theta in shared memory for the vector path: lane l of a warp multiplies the four samples 4l .. 4l+3 of every
+// 128-feature group, i.e. 32 bytes of theta per lane -- at that stride two 16-byte reads per lane collide four ways
+// (ncu: 55 % of the shared-memory wavefronts were conflicts and the kernel sat at 3.9 TB/s).  Stored as two planes
+// per group, {theta[4l], theta[4l+1]} for all lanes then {theta[4l+2], theta[4l+3]}, each read is one conflict-free
+// 16-byte access per lane.
+__device__ __forceinline__ int theta_slot(int e) {
+  const int g = e >> 7, r = e & 127, l = r >> 2, k = r & 3;
+  return (g << 7) + ((k >> 1) << 6) + (l << 1) + (k & 1);
+}
+
 template <int DOTK>
 __global__ void __launch_bounds__(kLossThreads) loss_f32_kernel(const LossF32Params p) {
   extern __shared__ double sm[];
-  double* sm_params = sm;                           // [intercept] + d, padded to a multiple of 4
-  double* sm_red = sm + ((p.d + 1 + 3) & ~3) + 4;   // 2 * nwarps
-  const int np = p.d + (p.intercept ? 1 : 0);
-  for (int i = threadIdx.x; i < np; i += blockDim.x) sm_params[i + (p.intercept ? 0 : 1)] = p.params[i];
+  const int dpad = (p.d + 127) & ~127;
+  double* th = sm;                                  // theta, dpad doubles (permuted when p.vec), 16-byte aligned
+  double* sm_red = sm + dpad + 2;                   // 2 * nwarps
+  for (int i = threadIdx.x; i < dpad; i += blockDim.x) th[i] = 0.0;
   __syncthreads();
-  const double* th = sm_params + 1;                 // theta[0..d), 8-byte aligned
-  const double b0 = p.intercept ? sm_params[0] : 0.0;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) th[p.vec ? theta_slot(i) : i] = p.params[i + (p.intercept ? 1 : 0)];
+  __syncthreads();
+  const double b0 = p.intercept ? p.params[0] : 0.0;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
   const int64_t warp_id = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -618,13 +629,16 @@ __global__ void __launch_bounds__(kLossThreads) loss_f32_kernel(const LossF32Par
           const int j = j0 + u * 128 + lane * 4;
           if (j < p.d) {
             const double xv[4] = {f32_to_f64(x[u].x), f32_to_f64(x[u].y), f32_to_f64(x[u].z), f32_to_f64(x[u].w)};
+            const double2 t01 = *reinterpret_cast<const double2*>(th + (j0 + u * 128) + lane * 2);
+            const double2 t23 = *reinterpret_cast<const double2*>(th + (j0 + u * 128) + 64 + lane * 2);
+            const double tv[4] = {t01.x, t01.y, t23.x, t23.y};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (DOTK == 2) {
-                const double t = th[j + k] - xv[k];
+                const double t = tv[k] - xv[k];
                 a = fma(t, t, a);
               } else {
-                a = fma(xv[k], th[j + k], a);
+                a = fma(xv[k], tv[k], a);
                 if (DOTK == 1) b = fma(xv[k], xv[k], b);
               }
             }
@@ -877,7 +891,7 @@ extern "C" int rlvi_loss_f32(rlvi_ctx* ctx, int kind, int intercept, const float
   p.vec = (rlvi_aligned16(X) && d % 4 == 0) ? 1 : 0;
   p.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + 128);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + 4096);
-  const size_t smem = (size_t((d + 1 + 3) & ~3) + 4 + 2 * warps_per_block) * sizeof(double);
+  const size_t smem = (size_t((d + 127) & ~127) + 2 + 2 * warps_per_block) * sizeof(double);
   if (kind == RLVI_LOSS_PCA) loss_f32_kernel<1><<<grid, kLossThreads, smem, st>>>(p);
   else if (kind == RLVI_LOSS_SQDIST) loss_f32_kernel<2><<<grid, kLossThreads, smem, st>>>(p);
   else loss_f32_kernel<0><<<grid, kLossThreads, smem, st>>>(p);

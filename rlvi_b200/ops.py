@@ -413,8 +413,22 @@ def em_step_logistic_host(X, y, params, *, tol=1e-3, maxiter=100, want_pi=True, 
     n, d = hx[1]
     if hy[1] != (n,) or hp[1] != (d + 1,):
         raise ValueError("shape mismatch: X [n,d], y [n], params [d+1]")
+    nm = _lib.load().rlvi_moments_out_doubles(d)
+
+    def chk_out(a, count, name):
+        """The C side copies `count` doubles into a raw host pointer: length, dtype and layout are checked here."""
+        if a is None:
+            return
+        if isinstance(a, torch.Tensor):
+            ok = (not a.is_cuda) and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == count
+        else:
+            ok = isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == count
+        if not ok:
+            raise ValueError(f"{name} must be a C-contiguous CPU float64 buffer of exactly {count} elements")
+
+    chk_out(pi_out, n, "pi_out")
+    chk_out(moments_out, nm, "moments_out")
     ctx = _lib.context(int(device))
-    nm = ctx.lib.rlvi_moments_out_doubles(d)
     if want_pi and pi_out is None:
         pi_out = np.empty(n, dtype=np.float64)
     if moments_out is None:

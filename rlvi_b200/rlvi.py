@@ -68,7 +68,9 @@ def update_weights_constrained(losses, n_eff, tol=1e-3, maxiter=100):
             return np.square(shift_sum(s) - n_eff)
 
         shift = _opt.minimize_scalar(shift_obj)["x"]             # rlvi.py:41
-        shift_sum(shift, pi_out=pi)                              # rlvi.py:42
+        # rlvi.py:42 -- the returned weights use the literal exp(-l + s): where e = exp(-l) has underflowed (l > ~708,
+        # far outliers of the Gaussian NLL) e * exp(s) would be 0 or imprecise although exp(-l + s) is representable
+        ops.shift_sum(l, shift, c, pi_out=pi, out=acc)
     return to_caller(pi, was_np)
 
 

@@ -209,3 +209,15 @@ def test_fp32_mode_calls_reach_the_f32_entry_points(rec):
         ops.weighted_moments(X, f64(n), center=f64(d))
     with pytest.raises(TypeError):
         ops.weighted_moments(X, f32(n))          # weights must be float64
+
+
+def test_host_entry_point_checks_its_output_buffers():
+    """rlvi_em_step_logistic_host copies n doubles of pi and the statistics into raw host pointers: a short, float32
+    or strided buffer must be refused before the call."""
+    import numpy as np
+    X, y, params = np.zeros((8, 4)), np.zeros(8), np.zeros(5)
+    for bad in (np.zeros(7), np.zeros(8, dtype=np.float32), np.zeros(16)[::2]):
+        with pytest.raises(ValueError, match="pi_out"):
+            ops.em_step_logistic_host(X, y, params, pi_out=bad)
+    with pytest.raises(ValueError, match="moments_out"):
+        ops.em_step_logistic_host(X, y, params, moments_out=np.zeros(3))

@@ -114,3 +114,58 @@ def test_sigmoid_any_size_and_online_cross_entropy(mods):
     lp = -rng.random(100)
     t = (rng.random(100) < 0.5).astype(np.float64)
     assert np.array_equal(mods.online.cross_entropy(lp, t), rlvi_np.online_cross_entropy(lp, t))
+
+
+def test_constrained_estep_outliers_whose_e_underflows(mods):
+    """the Brent objective runs on the cached e = exp(-l), but the RETURNED weights use the literal
+    exp(-l + s) of rlvi.py:42 -- far outliers (l > 708, e denormal or 0) keep their tiny but representable weights."""
+    rng = np.random.default_rng(31)
+    losses = np.concatenate([25.0 + 0.5 * rng.chisquare(1, size=2000), [730.0, 741.0]])
+    n_eff = 0.9 * len(losses)
+    pi = mods.rlvi.update_weights_constrained(losses, n_eff)
+    ref = rlvi_np.update_weights_constrained(losses, n_eff)
+    assert relmax(pi, ref) < 1e-6                               # Brent's own accuracy (SURVEY.md H4)
+    assert np.all(ref[-2:] > 0) and np.all(pi[-2:] > 0)
+    assert np.max(np.abs(pi[-2:] / ref[-2:] - 1)) < 1e-5        # element-wise on the two outliers (denormal e would be ~1e-2 off)
+
+
+def test_linear_regression_conditioning_bound(mods):
+    """the M-step solves the d x d normal equations, so the error grows like cond(X)^2 eps where the
+    reference's gelsd grows like cond(X) eps.  cond(X) = 1e3: still 1e-9; cond(X) = 1e5: bounded by 100 cond^2 eps."""
+    rng = np.random.default_rng(32)
+    n, d = 4000, 8
+    U, _ = np.linalg.qr(rng.normal(size=(n, d)))
+    V, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    for cond, bound in ((1e3, 1e-9), (1e5, 100 * 1e10 * 2.2e-16)):
+        X = (U * np.geomspace(1.0, 1.0 / cond, d)) @ V.T * np.sqrt(n)
+        y = X @ np.ones(d) + 0.1 * rng.normal(size=n)
+        assert relmax(mods.rlvi.linear_regression(X, y), rlvi_np.linear_regression(X, y)) < bound
+
+
+@pytest.mark.gpu
+def test_wce_invalid_label_or_index_poisons_instead_of_reading_out_of_bounds():
+    """a label outside [0, C) (ignore_index = -100, a corrupted label) or an index outside [0, n_train) raises
+    in the reference; the kernel never touches memory out of bounds and turns the row -- and the batch loss -- into NaN."""
+    from rlvi_b200 import ops
+    dev = torch.device("cuda", 0)
+    b, c, n_train = 64, 10, 100
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(b, c, generator=g).to(dev)
+    labels = torch.randint(0, c, (b,), generator=g).to(dev)
+    idx = torch.randperm(n_train, generator=g)[:b].to(dev)
+    w = torch.rand(n_train, generator=g).to(dev)
+    res = torch.full((n_train + 8,), 7.0, device=dev)[:n_train]          # guard band behind the view
+    ok = ops.wce_fwd_bwd(logits, labels, w, res, indexes=idx, want_per_sample=True)
+    assert torch.isfinite(ok["loss"]).all() and torch.isfinite(ok["dlogits"]).all()
+    bad_labels = labels.clone()
+    bad_labels[3], bad_labels[17] = -100, c + 5
+    out = ops.wce_fwd_bwd(logits, bad_labels, w, res.clone(), indexes=idx, want_per_sample=True)
+    assert torch.isnan(out["loss"]).all() and torch.isnan(out["per_sample"][[3, 17]]).all()
+    assert torch.isnan(out["dlogits"][[3, 17]]).all()
+    keep = torch.ones(b, dtype=torch.bool, device=dev)
+    keep[[3, 17]] = False
+    assert torch.equal(out["dlogits"][keep], ok["dlogits"][keep]) and torch.equal(out["per_sample"][keep], ok["per_sample"][keep])
+    bad_idx = idx.clone()
+    bad_idx[5] = n_train + 3
+    out = ops.wce_fwd_bwd(logits, labels, w, res.clone(), indexes=bad_idx)
+    assert torch.isnan(out["loss"]).all()
