@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(256) add_f64_kernel(double* __restrict__ dst, 
 
 }  // namespace
 
+size_t rlvi_tf32_pair_scratch_bytes(int sm_count, int64_t n, int power, bool has_y);   // gram_tf32_pair.cu
 int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap3, tf32::Tf32Params p, int precision,
                            int want_gram, double* out, cudaStream_t st);   // gram_tf32_pair.cu
 
@@ -724,10 +725,14 @@ extern "C" int rlvi_weighted_moments_f32(rlvi_ctx* ctx, const float* X, const do
   const size_t pbytes = size_t(grid) * sizeof(unsigned int);
   // sized for one CTA per SM whichever kernel runs (the pair path lays its own partials out in the same scratch, and
   // the scratch must not move once the weight-maximum kernel below has been queued)
-  const size_t per_cta = size_t(2) * kMB * kMB * sizeof(double) + size_t(kTeams) * 2 * 128 * sizeof(double) +
-                         size_t(kTeams) * 2 * sizeof(double) + sizeof(unsigned int);
+  const size_t per_cta = size_t(2) * kMB * kMB * sizeof(double) + size_t(8) * 2 * 128 * sizeof(double) +
+                         size_t(8) * 2 * sizeof(double) + sizeof(unsigned int);      // up to 8 column-sum workers per CTA
   size_t need = 4096 + gbytes + sbytes + s0bytes + pbytes;
   if (need < 4096 + per_cta * size_t(ctx->sm_count)) need = 4096 + per_cta * size_t(ctx->sm_count);
+  {
+    const size_t pair_need = rlvi_tf32_pair_scratch_bytes(ctx->sm_count, n, power, y != nullptr);
+    if (p.nb >= 2 && need < pair_need) need = pair_need;
+  }
   void* scratch = nullptr;
   const int rc = rlvi_scratch(ctx, need, &scratch);
   if (rc != RLVI_OK) return rc;
@@ -748,7 +753,7 @@ extern "C" int rlvi_weighted_moments_f32(rlvi_ctx* ctx, const float* X, const do
     RLVI_LAUNCH_CHECK(ctx);
   }
 
-  {   // d = 129..256 and 385..512: CTA pairs (gram_tf32_pair.cu); anything else, or a device that cannot co-schedule pairs: below
+  {   // d = 129..512: CTA pairs (gram_tf32_pair.cu); d <= 128, or a device that cannot co-schedule pairs: below
     const int prc = rlvi_tf32_pair_moments(ctx, tmap, tmap3, p, precision, want_gram, out, st);
     if (prc != RLVI_ERR_UNSUPPORTED) return prc;
   }

@@ -36,13 +36,21 @@ using namespace tf32;
 
 constexpr int kPairStages = 12;             // upper bound; the ring uses min(kPairStages, budget / stage bytes)
 constexpr int kPairTypes = 3;
-constexpr int kCoefBytes = 256;             // per stage: pi of the tile's 16 rows (128 B) + y (128 B)
+constexpr int kWorkers = 6;                 // transform warps per CTA: warps 2-7
+constexpr int kCoefBytes = 256;             // per stage: s, c1, cy of the tile's 16 rows (64 B each)
+constexpr int kCoefThreads = 256;
 
 struct PairParams {
   Tf32Params b;                 // w, y, n, d, power, chunks_per_flush, box3d, partials, err, wmax, stats
   int nbp;                      // 256-feature pair blocks: 1 or 2
   int ntypes;                   // 1 or 3
   int first[kPairTypes + 1];    // first pair of each type; first[ntypes] = number of pairs (grid = 2 x that)
+  // per-row FP32 coefficients written by pair_coef_kernel (padded with zeros to a multiple of kR rows):
+  const float* coef_sc;         // s_i: z_i = s_i x_i
+  const float* coef_c1;         // the X^T pi coefficient; == coef_sc for power 2
+  const float* coef_cy;         // the X^T (w y) coefficient, or null
+  double* s0blocks;             // [coef_blocks][2] partial S0 / Swy of the coefficient kernel
+  int coef_blocks;
 };
 
 __host__ __device__ __forceinline__ void pair_type(int t, int nbp, int& pa, int& pb) {
@@ -132,261 +140,203 @@ struct PairCtx {
   unsigned char* smem;
   uint64_t *full_bar, *empty_bar, *tfull_bar;
   uint32_t ready_remote, tempty_remote;    // the LEADER's `ready[0]` / `tempty[0]` as shared::cluster addresses
-  float* red_all;
-  double* dred_all;
+  float* red_all;            // [kWorkers][2][128] column-sum exchange, private to each transform warp
   uint32_t tmem_base;
-  int stage_bytes, nst, nfb, slot, nslots, team;
+  int stage_bytes, nst, nfb, slot, nslots;
   int my_tiles, my_chunks;
-  bool own_s0;
-  bool coef_bulk;            // the producer copies the tile's pi (and y) into the stage's coefficient slot
+  bool c1_is_sc;             // power 2: the column-sum coefficient is the row scale itself
   uint32_t coef_off;         // byte offset of the coefficient slots (kCoefBytes per stage) behind the stages
 };
 
-// One transform team (four warps): tiles team, team + 3, ... of the CTA.  IS_ACC teams (1, 2) own the level-2
-// accumulators of column half team - 1.  HAS_SUMS (diagonal pairs): the column sums of the CTA's feature block ride along.
-template <int NSPLIT, bool HAS_Y, bool IS_ACC, bool HAS_SUMS>
-__device__ __forceinline__ void pair_team_body(const Tf32Params& p, const PairCtx& cx) {
+// One TRANSFORM warp (worker w of kWorkers): tiles w, w + kWorkers, ... of the CTA, in place on the landed tile:
+// z = s_i x rounded to TF32 (Z_hi) and, for 3xTF32, the remainder Z_lo into the second buffer; with HAS_SUMS (diagonal
+// pairs) the column sums of the CTA's feature block ride along.  Single warps (not four-warp teams): a tile's transform
+// is a chain of dependent shared-memory round trips whose latency triples under load, so what counts is how many
+// tiles are in flight, and a warp needs no barrier but __syncwarp.
+template <int NSPLIT, bool HAS_Y, bool HAS_SUMS>
+__device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const PairCtx& cx, const int worker) {
   unsigned char* smem = cx.smem;
-  uint64_t *full_bar = cx.full_bar, *tfull_bar = cx.tfull_bar, *empty_bar = cx.empty_bar;
-  const uint32_t tmem_base = cx.tmem_base;
-  const int stage_bytes = cx.stage_bytes, nst = cx.nst, nfb = cx.nfb, slot = cx.slot, team = cx.team;
-  const int my_tiles = cx.my_tiles, my_chunks = cx.my_chunks;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tt = threadIdx.x & 127;                      // thread of the team
-  const int q = tt & 7, rr = tt >> 3;                    // logical 16-byte unit, row of the tile
-  // SWIZZLE_128B_ATOM_32B: the 32-byte unit q >> 1 of row rr sits at unit (q >> 1) ^ (rr & 3)
-  const uint32_t off = uint32_t(rr * 128 + (((((q >> 1) ^ (rr & 3)) << 1) | (q & 1)) << 4));
+  uint64_t *full_bar = cx.full_bar, *empty_bar = cx.empty_bar;
+  const int stage_bytes = cx.stage_bytes, nst = cx.nst, nfb = cx.nfb, slot = cx.slot;
+  const int my_tiles = cx.my_tiles;
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7, r4 = lane >> 3;                // logical 16-byte unit, row within a pass of 4 rows
+  // SWIZZLE_128B_ATOM_32B: the 32-byte unit q >> 1 of row rr sits at unit (q >> 1) ^ (rr & 3); rr & 3 = r4 in every pass
+  const uint32_t off0 = uint32_t(r4 * 128 + (((((q >> 1) ^ r4) << 1) | (q & 1)) << 4));
   const uint32_t lo_off = uint32_t(nfb * kBlkBytes);
-  const bool own_s0 = cx.own_s0 && (q == 0);
-  float* red = cx.red_all + team * 1024;
-  double* dred = cx.dred_all + team * 32;
-  const int bar_id = 1 + team;
-  float s1acc[HAS_SUMS ? 4 : 1][4], syacc[(HAS_SUMS && HAS_Y) ? 4 : 1][4];
+  float* red = cx.red_all + worker * 256;
+  float2 s1acc[HAS_SUMS ? 4 : 1][2], syacc[(HAS_SUMS && HAS_Y) ? 4 : 1][2];       // [chunk][float pair of the 16-byte unit]
 #pragma unroll
-  for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c)
+  for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c) s1acc[c][0] = s1acc[c][1] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s1acc[c][k] = 0.f;
-#pragma unroll
-  for (int c = 0; c < ((HAS_SUMS && HAS_Y) ? 4 : 1); ++c)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) syacc[c][k] = 0.f;
-  double s1d = 0.0, syd = 0.0, s0 = 0.0, swy = 0.0;
-  const double wscale = ldexp(1.0, -weight_exponent(p.wmax));      // exact power of two
-
-  // ---- accumulator state (teams 1, 2: column half h = team - 1; thread = TMEM lane quarter * 32 + lane) ----
-  const int h = team - 1;
-  const int quarter = warp & 3;                          // hardware: a warp reaches TMEM lanes 32 (warp id % 4) ..
-  float acc[IS_ACC ? 128 : 2];
-#pragma unroll
-  for (int i = 0; i < (IS_ACC ? 128 : 2); ++i) acc[i] = 0.f;
-  double* gp = p.gpart64 + ((size_t(blockIdx.x) * 2 + (IS_ACC ? h : 0)) * 128 + size_t(quarter * 32 + lane)) * 128;
-  bool flushed = false;
-  int next_drain = 0;
+  for (int c = 0; c < ((HAS_SUMS && HAS_Y) ? 4 : 1); ++c) syacc[c][0] = syacc[c][1] = make_float2(0.f, 0.f);
+  double s1d[4] = {0.0, 0.0, 0.0, 0.0}, syd[4] = {0.0, 0.0, 0.0, 0.0};
   bool ok = true;
 
-  auto flush_acc = [&]() {
-    if (IS_ACC) {
+  // FP32 column sums of the last kFlushTiles tiles -> FP64 (lane l keeps columns l, l + 32, l + 64, l + 96)
+  auto flush_sums = [&]() {
+    if (HAS_SUMS) {
 #pragma unroll
-      for (int i = 0; i < (IS_ACC ? 128 : 2); i += 2) {
-        double2 v = make_double2(double(acc[i]), double(acc[i + 1]));
-        if (flushed) {
-          const double2 o = *reinterpret_cast<const double2*>(gp + i);
-          v.x += o.x;
-          v.y += o.y;
+      for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = (k & 1) ? s1acc[c][k >> 1].y : s1acc[c][k >> 1].x;
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 8) red[c * 32 + lane * 4 + k] = v;
+          if (HAS_Y) {
+            float u = (k & 1) ? syacc[(HAS_SUMS && HAS_Y) ? c : 0][k >> 1].y : syacc[(HAS_SUMS && HAS_Y) ? c : 0][k >> 1].x;
+            u += __shfl_xor_sync(0xffffffffu, u, 8);
+            u += __shfl_xor_sync(0xffffffffu, u, 16);
+            if (lane < 8) red[128 + c * 32 + lane * 4 + k] = u;
+          }
         }
-        *reinterpret_cast<double2*>(gp + i) = v;
-        acc[i] = 0.f;
-        acc[i + 1] = 0.f;
+#pragma unroll
+      for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c) s1acc[c][0] = s1acc[c][1] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < ((HAS_SUMS && HAS_Y) ? 4 : 1); ++c) syacc[c][0] = syacc[c][1] = make_float2(0.f, 0.f);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s1d[j] += double(red[j * 32 + lane]);
+        if (HAS_Y) syd[j] += double(red[128 + j * 32 + lane]);
       }
+      __syncwarp();
+    }
+  };
+
+  int done = 0;
+  long long t_full = 0, t_busy = 0;
+  int s = worker % nst;
+  uint32_t ph = uint32_t(worker / nst) & 1u;
+  for (int it = worker; it < my_tiles; it += kWorkers) {
+    const long long k1 = p.stats ? clock64() : 0;
+    // see gram_tf32.cu: `empty` one phase back first, so that `full` cannot be mistaken for the previous phase
+    ok = wait_or_abort(&empty_bar[s], ph ^ 1u, p.err) && wait_or_abort(&full_bar[s], ph, p.err);
+    if (!ok) break;
+    const long long k2 = p.stats ? clock64() : 0;
+    t_full += k2 - k1;
+    unsigned char* sb = smem + size_t(s) * stage_bytes;
+    // the tile's row coefficients arrived with it (FP32, from pair_coef_kernel): no FP64 and no global load in this loop --
+    // FP64 instructions issued while the tensor pipe is busy wait for it (stall_math was 47 % of these warps' time)
+    const float* cf = reinterpret_cast<const float*>(smem + cx.coef_off + uint32_t(s) * kCoefBytes);
+#pragma unroll
+    for (int pass = 0; pass < kR / 4; ++pass) {
+      const int rr = pass * 4 + r4;
+      const float sc = cf[rr];
+      const float c1 = cx.c1_is_sc ? sc : cf[kR + rr];
+      const float cy = HAS_Y ? cf[2 * kR + rr] : 0.f;
+      const float2 scv = make_float2(sc, sc), c1v = make_float2(c1, c1), cyv = make_float2(cy, cy), m1v = make_float2(-1.f, -1.f);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i < nfb) {
+          const bool sums = HAS_SUMS && (i == 0);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4* ptr = reinterpret_cast<float4*>(sb + i * kBlkBytes + c * kChunkBytes + pass * 512 + off0);
+            const float4 x = *ptr;
+            const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+            if (sums) {
+              s1acc[HAS_SUMS ? c : 0][0] = f2fma(xa, c1v, s1acc[HAS_SUMS ? c : 0][0]);
+              s1acc[HAS_SUMS ? c : 0][1] = f2fma(xb, c1v, s1acc[HAS_SUMS ? c : 0][1]);
+              if (HAS_Y) {
+                syacc[(HAS_SUMS && HAS_Y) ? c : 0][0] = f2fma(xa, cyv, syacc[(HAS_SUMS && HAS_Y) ? c : 0][0]);
+                syacc[(HAS_SUMS && HAS_Y) ? c : 0][1] = f2fma(xb, cyv, syacc[(HAS_SUMS && HAS_Y) ? c : 0][1]);
+              }
+            }
+            const float2 za = f2mul(xa, scv), zb = f2mul(xb, scv);
+            const float2 ha = tf32_hi2(za), hb = tf32_hi2(zb);
+            *ptr = make_float4(ha.x, ha.y, hb.x, hb.y);
+            if (NSPLIT == 3) {
+              const float2 la = f2fma(ha, m1v, za), lb = f2fma(hb, m1v, zb);       // exact remainders
+              *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ptr) + lo_off) = make_float4(la.x, la.y, lb.x, lb.y);
+            }
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(cx.ready_remote + uint32_t(s) * 8u);   // the leader's barrier: 1 + 1 warps per tile
+    if ((++done % kFlushTiles) == 0) flush_sums();
+    s += kWorkers;
+    while (s >= nst) {
+      s -= nst;
+      ph ^= 1u;
+    }
+    if (p.stats) t_busy += clock64() - k2;
+  }
+  if (p.stats && lane == 0 && worker == 0) {
+    p.stats[size_t(blockIdx.x) * 8 + 1] = t_full * kWorkers;      // scaled to "per tile of the CTA" like the other roles
+    p.stats[size_t(blockIdx.x) * 8 + 2] = t_busy * kWorkers;
+  }
+  if (ok) {
+    flush_sums();
+    if (HAS_SUMS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p.spart[((size_t(blockIdx.x) * kWorkers + worker) * 2 + 0) * 128 + j * 32 + lane] = s1d[j];
+        p.spart[((size_t(blockIdx.x) * kWorkers + worker) * 2 + 1) * 128 + j * 32 + lane] = syd[j];
+      }
+    }
+  }
+}
+
+// One ACCUMULATOR warp (warps 8-15): TMEM lanes 32 (warp % 4) .. + 31 of column half h = (warp - 8) / 4.  The tensor core
+// adds in FP32 with truncation, so a TMEM accumulator only lives for kTpc tiles; it is read back (tcgen05.ld) and
+// added, round-to-nearest, into 128 FP32 registers, themselves flushed into the CTA's FP64 partial every
+// `chunks_per_flush` chunks.  Two TMEM buffers alternate, so chunk c is drained while chunk c + 1 accumulates.
+__device__ __forceinline__ void pair_acc_warp(const Tf32Params& p, const PairCtx& cx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = (warp - 8) >> 2, quarter = warp & 3;
+  float acc[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+  double* gp = p.gpart64 + ((size_t(blockIdx.x) * 2 + h) * 128 + size_t(quarter * 32 + lane)) * 128;
+  bool flushed = false;
+  bool ok = true;
+  long long t_drain = 0;
+  auto flush_acc = [&]() {
+#pragma unroll
+    for (int i = 0; i < 128; i += 2) {
+      double2 v = make_double2(double(acc[i]), double(acc[i + 1]));
+      if (flushed) {
+        const double2 o = *reinterpret_cast<const double2*>(gp + i);
+        v.x += o.x;
+        v.y += o.y;
+      }
+      *reinterpret_cast<double2*>(gp + i) = v;
+      acc[i] = 0.f;
+      acc[i + 1] = 0.f;
     }
     flushed = true;
   };
-  auto drain = [&](int ch) -> bool {
+  for (int ch = 0; ch < cx.my_chunks; ++ch) {
     const int buf = ch & 1;
-    if (!wait_or_abort(&tfull_bar[buf], uint32_t(ch >> 1) & 1u, p.err)) return false;
+    if (!wait_or_abort(&cx.tfull_bar[buf], uint32_t(ch >> 1) & 1u, p.err)) {
+      ok = false;
+      break;
+    }
+    const long long k0 = p.stats ? clock64() : 0;
     tc_fence_after();
-    if (IS_ACC && !(p.window & 4)) {
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * 256 + h * 128);
+    {
+      const uint32_t taddr = cx.tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * 256 + h * 128);
 #pragma unroll
-      for (int c = 0; c < (IS_ACC ? 8 : 0); ++c) {
+      for (int c = 0; c < 8; ++c) {
         float v[16];
         tc_ld16(taddr + uint32_t(c * 16), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[(c * 16 + j) % (IS_ACC ? 128 : 2)] += v[j];
+        for (int j = 0; j < 16; ++j) acc[c * 16 + j] += v[j];
       }
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(cx.tempty_remote + uint32_t(buf) * 8u);
     if (((ch + 1) % p.chunks_per_flush) == 0) flush_acc();
-    return true;
-  };
-
-  auto flush_sums = [&]() {
-    if (HAS_SUMS) {
-      const int wq = tt >> 5;
-#pragma unroll
-      for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float v = s1acc[c][k];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (lane < 8) red[(wq * 2 + 0) * 128 + c * 32 + lane * 4 + k] = v;
-          s1acc[c][k] = 0.f;
-          if (HAS_Y) {
-            float u = syacc[(HAS_SUMS && HAS_Y) ? c : 0][k];
-            u += __shfl_xor_sync(0xffffffffu, u, 8);
-            u += __shfl_xor_sync(0xffffffffu, u, 16);
-            if (lane < 8) red[(wq * 2 + 1) * 128 + c * 32 + lane * 4 + k] = u;
-            syacc[(HAS_SUMS && HAS_Y) ? c : 0][k] = 0.f;
-          }
-        }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      s1d += double((red[0 * 128 + tt] + red[2 * 128 + tt]) + (red[4 * 128 + tt] + red[6 * 128 + tt]));
-      if (HAS_Y) syd += double((red[1 * 128 + tt] + red[3 * 128 + tt]) + (red[5 * 128 + tt] + red[7 * 128 + tt]));
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-    }
-  };
-
-  // Row coefficients: the producer's bulk copy delivers pi (and y) of a full tile with the tile itself (no global-load
-  // latency in this loop: it was THE bound of the single-CTA kernel, profiles/r02_tf32_pair_ablation.txt); only a
-  // ragged last tile, or unaligned pi / y, is read from global memory here.
-  auto load_row = [&](int it, double& pid, double& yd) {
-    const int64_t row = (int64_t(slot) + int64_t(it) * cx.nslots) * kR + rr;
-    pid = (it < my_tiles && row < p.n) ? p.w[row] : 0.0;
-    yd = (HAS_Y && it < my_tiles && row < p.n) ? p.y[row] : 0.0;
-  };
-
-  int done = 0;
-  long long t_full = 0, t_busy = 0, t_drain = 0, t_a = 0, t_b = 0, t_c = 0, t_d = 0, t_e = 0;
-  int s = team % nst;
-  uint32_t ph = uint32_t(team / nst) & 1u;
-  for (int it = team; it < my_tiles; it += kTeams) {
-    const bool in_smem = cx.coef_bulk && ((int64_t(slot) + int64_t(it) * cx.nslots + 1) * kR <= p.n);
-    double pid = 0.0, yd = 0.0;
-    if (!in_smem) load_row(it, pid, yd);
-    const long long k0 = p.stats ? clock64() : 0;
-    if (IS_ACC) {                                        // chunk c - 2 is complete by now: drain it before chunk c
-      const int ch = it / kTpc;
-      while (ok && next_drain + 2 <= ch) ok = drain(next_drain++);
-      if (!ok) break;
-    }
-    const long long k1 = p.stats ? clock64() : 0;
-    // see gram_tf32.cu: `empty` one phase back first, so that `full` cannot be mistaken for the previous phase
-    ok = wait_or_abort(&empty_bar[s], ph ^ 1u, p.err) && wait_or_abort(&full_bar[s], ph, p.err);
-    if (!ok) break;
-    const long long k2 = p.stats ? clock64() : 0;
-    t_drain += k1 - k0;
-    t_full += k2 - k1;
-    unsigned char* sb = smem + size_t(s) * stage_bytes;
-    if (in_smem) {
-      const double* cw = reinterpret_cast<const double*>(smem + cx.coef_off + uint32_t(s) * kCoefBytes);
-      pid = cw[rr];
-      if (HAS_Y) yd = cw[kR + rr];
-    }
-    const double wd = (p.power == 2) ? pid * pid : pid;
-    const double pis = pid * wscale;                       // normalised weight, <= 1
-    const float sc = (p.power == 2) ? float(pis) : float(sqrt(pis));
-    const float c1 = float(pis);
-    const float cy = HAS_Y ? float(((p.power == 2) ? pis * pis : pis) * yd) : 0.f;
-    if (own_s0) {
-      s0 += wd;
-      if (HAS_Y) swy = fma(wd, yd, swy);
-    }
-    const long long k3 = p.stats ? clock64() : 0;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (i < nfb && !(p.window & 2)) {
-        const bool sums = HAS_SUMS && (i == 0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float4* ptr = reinterpret_cast<float4*>(sb + i * kBlkBytes + c * kChunkBytes + off);
-          const float4 x = *ptr;
-          if (sums) {
-            s1acc[HAS_SUMS ? c : 0][0] = fmaf(c1, x.x, s1acc[HAS_SUMS ? c : 0][0]);
-            s1acc[HAS_SUMS ? c : 0][1] = fmaf(c1, x.y, s1acc[HAS_SUMS ? c : 0][1]);
-            s1acc[HAS_SUMS ? c : 0][2] = fmaf(c1, x.z, s1acc[HAS_SUMS ? c : 0][2]);
-            s1acc[HAS_SUMS ? c : 0][3] = fmaf(c1, x.w, s1acc[HAS_SUMS ? c : 0][3]);
-            if (HAS_Y) {
-              syacc[(HAS_SUMS && HAS_Y) ? c : 0][0] = fmaf(cy, x.x, syacc[(HAS_SUMS && HAS_Y) ? c : 0][0]);
-              syacc[(HAS_SUMS && HAS_Y) ? c : 0][1] = fmaf(cy, x.y, syacc[(HAS_SUMS && HAS_Y) ? c : 0][1]);
-              syacc[(HAS_SUMS && HAS_Y) ? c : 0][2] = fmaf(cy, x.z, syacc[(HAS_SUMS && HAS_Y) ? c : 0][2]);
-              syacc[(HAS_SUMS && HAS_Y) ? c : 0][3] = fmaf(cy, x.w, syacc[(HAS_SUMS && HAS_Y) ? c : 0][3]);
-            }
-          }
-          const float z0 = sc * x.x, z1 = sc * x.y, z2 = sc * x.z, z3 = sc * x.w;
-          const uint32_t h0 = to_tf32(z0), h1 = to_tf32(z1), h2 = to_tf32(z2), h3 = to_tf32(z3);
-          *reinterpret_cast<uint4*>(ptr) = make_uint4(h0, h1, h2, h3);
-          if (NSPLIT == 3) {
-            const uint32_t l0 = to_tf32(z0 - __uint_as_float(h0)), l1 = to_tf32(z1 - __uint_as_float(h1)),
-                           l2 = to_tf32(z2 - __uint_as_float(h2)), l3 = to_tf32(z3 - __uint_as_float(h3));
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(ptr) + lo_off) = make_uint4(l0, l1, l2, l3);
-          }
-        }
-      }
-    }
-    const long long k4 = p.stats ? clock64() : 0;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
-    const long long k5 = p.stats ? clock64() : 0;
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(cx.ready_remote + uint32_t(s) * 8u);   // the leader's barrier: 4 + 4 warps per tile
-    const long long k6 = p.stats ? clock64() : 0;
-    if ((++done % kFlushTiles) == 0) flush_sums();
-    if (p.stats) {
-      const long long k7 = clock64();
-      t_a += k3 - k2;
-      t_b += k4 - k3;
-      t_c += k5 - k4;
-      t_d += k6 - k5;
-      t_e += k7 - k6;
-    }
-    s += kTeams;                                           // nst >= 4 > kTeams: at most one wrap
-    if (s >= nst) {
-      s -= nst;
-      ph ^= 1u;
-    }
-    if (p.stats) t_busy += clock64() - k2;
+    if (p.stats) t_drain += clock64() - k0;
   }
-  if (p.stats && tt == 0 && team < 2) {
-    p.stats[size_t(blockIdx.x) * 8 + (team == 0 ? 1 : 6)] = (team == 0) ? t_full : t_drain;
-    if (team == 0) p.stats[size_t(blockIdx.x) * 8 + 2] = t_busy;
-    if (team == 0) {
-      long long* x = p.stats + size_t(gridDim.x) * 8 + size_t(blockIdx.x) * 8;
-      x[0] = t_a;
-      x[1] = t_b;
-      x[2] = t_c;
-      x[3] = t_d;
-      x[4] = t_e;
-    }
-  }
-  if (ok) {
-    flush_sums();
-    if (HAS_SUMS) {
-      p.spart[((size_t(blockIdx.x) * kTeams + team) * 2 + 0) * 128 + tt] = s1d;
-      p.spart[((size_t(blockIdx.x) * kTeams + team) * 2 + 1) * 128 + tt] = syd;
-    }
-    if (cx.own_s0) {
-      if (q == 0) {
-        dred[rr * 2 + 0] = s0;
-        dred[rr * 2 + 1] = swy;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (tt == 0) {
-        double a = 0.0, b = 0.0;
-        for (int r = 0; r < kR; ++r) {
-          a += dred[r * 2 + 0];
-          b += dred[r * 2 + 1];
-        }
-        p.s0part[(size_t(blockIdx.x) * kTeams + team) * 2 + 0] = a;
-        p.s0part[(size_t(blockIdx.x) * kTeams + team) * 2 + 1] = b;
-      }
-    }
-    if (IS_ACC) {
-      while (ok && next_drain < my_chunks) ok = drain(next_drain++);
-      if (ok) flush_acc();
-    }
-  }
+  if (p.stats && lane == 0 && warp == 8) p.stats[size_t(blockIdx.x) * 8 + 6] = t_drain * kTpc;   // per chunk -> per 8 tiles
+  if (ok) flush_acc();
 }
 
 template <int NSPLIT, bool HAS_Y>
@@ -405,8 +355,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* tfull_bar = empty_bar + kPairStages;                    // [2] MMA -> accumulator warps (multicast)
   uint64_t* tempty_bar = tfull_bar + 2;                             // [2] accumulator warps (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* red_all = reinterpret_cast<float*>(tail + 512);            // [kTeams][4 warps][2][128] column-sum exchange
-  double* dred_all = reinterpret_cast<double*>(tail + 512 + kTeams * 4096);   // [kTeams][16][2] S0 / Swy exchange
+  float* red_all = reinterpret_cast<float*>(tail + 512);            // [kWorkers][2][128] column-sum exchange (per warp)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -425,7 +374,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   int nst = (kSmemBudget - kPairStages * kCoefBytes) / stage_bytes;
   if (nst > kPairStages) nst = kPairStages;
   const uint32_t coef_off = uint32_t(nst) * uint32_t(stage_bytes);      // coefficient slots behind the stages
-  const bool coef_bulk = ((reinterpret_cast<uintptr_t>(p.w) | reinterpret_cast<uintptr_t>(p.y)) & 15u) == 0u;
   const int ntiles = int((p.n + kR - 1) / kR);
   const int my_tiles = (ntiles > slot) ? (ntiles - slot + nslots - 1) / nslots : 0;
   const int my_chunks = (my_tiles + kTpc - 1) / kTpc;
@@ -433,7 +381,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 8);      // 4 transform warps of each CTA per tile
+      mbar_init(&ready_bar[s], 2);      // the tile's transform warp of each CTA
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -453,9 +401,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp < 4) {
-    // ===== warpgroup 0: TMA producer (warp 0, both CTAs) and MMA issuer (warp 1 of the leader) ====================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  PairCtx cx;
+  cx.smem = smem;
+  cx.full_bar = full_bar;
+  cx.empty_bar = empty_bar;
+  cx.tfull_bar = tfull_bar;
+  cx.ready_remote = map_to_cta(smem_u32(ready_bar), 0u);
+  cx.tempty_remote = map_to_cta(smem_u32(tempty_bar), 0u);
+  cx.red_all = red_all;
+  cx.tmem_base = tmem_base;
+  cx.stage_bytes = stage_bytes;
+  cx.nst = nst;
+  cx.nfb = nfb;
+  cx.slot = slot;
+  cx.nslots = nslots;
+  cx.my_tiles = my_tiles;
+  cx.my_chunks = my_chunks;
+  cx.c1_is_sc = (pp.coef_c1 == pp.coef_sc);
+  cx.coef_off = coef_off;
+
+  if (warp < 8) {
+    // ===== warpgroups 0, 1: TMA producer (warp 0, both CTAs), MMA issuer (warp 1 of the leader), six transform warps ======
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0 && lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -471,17 +438,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         t_wait += clock64() - c0;
         const int row0 = (slot + it * nslots) * kR;
         const uint32_t sb = smem_base + uint32_t(s) * uint32_t(stage_bytes);
-        const bool coef = coef_bulk && (int64_t(row0) + kR <= p.n);
-        const uint32_t coef_tx = coef ? uint32_t(kR * 8 * (HAS_Y ? 2 : 1)) : 0u;
-        mbar_arrive_expect_tx(&full_bar[s], ((p.window & 8) ? 0u : uint32_t(nfb * kBlkBytes)) + coef_tx);
-        if (coef) {
+        const bool c1_sep = (pp.coef_c1 != pp.coef_sc);
+        const uint32_t coef_tx = uint32_t(kR * 4) * (1u + (c1_sep ? 1u : 0u) + (HAS_Y ? 1u : 0u));
+        mbar_arrive_expect_tx(&full_bar[s], uint32_t(nfb * kBlkBytes) + coef_tx);
+        {
           unsigned char* cdst = smem + coef_off + uint32_t(s) * kCoefBytes;
-          bulk_g2s(cdst, p.w + row0, kR * 8, &full_bar[s]);
-          if (HAS_Y) bulk_g2s(cdst + kR * 8, p.y + row0, kR * 8, &full_bar[s]);
+          bulk_g2s(cdst, pp.coef_sc + row0, kR * 4, &full_bar[s]);
+          if (c1_sep) bulk_g2s(cdst + kR * 4, pp.coef_c1 + row0, kR * 4, &full_bar[s]);
+          if (HAS_Y) bulk_g2s(cdst + 2 * kR * 4, pp.coef_cy + row0, kR * 4, &full_bar[s]);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          if (i < nfb && !(p.window & 8)) {
+          if (i < nfb) {
             const int fbi = (i == 0) ? fb_a : fb_b;
             if (p.box3d) {       // one box: 32 floats x 16 rows x 4 column groups
               tma_load_3d_f32(sb + uint32_t(i * kBlkBytes), &tmap3, 0, row0, fbi * 4, &full_bar[s]);
@@ -541,7 +509,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t dcol = tmem_base + uint32_t(buf * 256);
 #pragma unroll
         for (int ks = 0; ks < kR / 8; ++ks) {
-          if (p.window & 1) break;
           const uint32_t first = (tin == 0 && ks == 0) ? 0u : 1u;
           const uint32_t kb = sb + uint32_t(ks * 1024);
           const uint64_t a_hi = desc(kb + a_off), b_hi = desc(kb + b_off);
@@ -564,39 +531,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         p.stats[size_t(blockIdx.x) * 8 + 4] = t_tempty;
         p.stats[size_t(blockIdx.x) * 8 + 5] = t_issue;
       }
+    } else if (warp >= 2) {
+      if (diag) pair_transform_warp<NSPLIT, HAS_Y, true>(p, cx, warp - 2);
+      else pair_transform_warp<NSPLIT, HAS_Y, false>(p, cx, warp - 2);
     }
   } else {
-    // ===== warpgroups 1-3: the transform teams; teams 1 and 2 also hold the level-2 accumulators ================
-    PairCtx cx;
-    cx.smem = smem;
-    cx.full_bar = full_bar;
-    cx.empty_bar = empty_bar;
-    cx.tfull_bar = tfull_bar;
-    cx.ready_remote = map_to_cta(smem_u32(ready_bar), 0u);
-    cx.tempty_remote = map_to_cta(smem_u32(tempty_bar), 0u);
-    cx.red_all = red_all;
-    cx.dred_all = dred_all;
-    cx.tmem_base = tmem_base;
-    cx.stage_bytes = stage_bytes;
-    cx.nst = nst;
-    cx.nfb = nfb;
-    cx.slot = slot;
-    cx.nslots = nslots;
-    cx.team = (warp >> 2) - 1;
-    cx.my_tiles = my_tiles;
-    cx.my_chunks = my_chunks;
-    cx.own_s0 = (type == 0 && rank == 0);
-    cx.coef_bulk = coef_bulk;
-    cx.coef_off = coef_off;
-    if (cx.team == 0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-      if (diag) pair_team_body<NSPLIT, HAS_Y, false, true>(p, cx);
-      else pair_team_body<NSPLIT, HAS_Y, false, false>(p, cx);
-    } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-      if (diag) pair_team_body<NSPLIT, HAS_Y, true, true>(p, cx);
-      else pair_team_body<NSPLIT, HAS_Y, true, false>(p, cx);
-    }
+    // ===== warpgroups 2, 3: the accumulator warps (TMEM -> FP32 registers -> FP64 partials) ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    pair_acc_warp(p, cx);
   }
 
   tc_fence_before();
@@ -604,6 +546,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();              // both CTAs are done with each other's shared memory, barriers and TMEM
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Row coefficients in FP32, once per call (HBM-bound, ~20 B per row): s_i = pi_i 2^-e (power 2) or sqrt(pi_i 2^-e)
+// (power 1) -- the factor of z_i = s_i x_i --, c1_i = pi_i 2^-e for X^T pi, cy_i = w_i y_i (normalised) for X^T (w y);
+// rows n .. npad - 1 are zero.  Also S0 = sum w_i and Swy = sum w_i y_i in FP64 (w = pi^2 or pi), as per-block partials.
+__global__ void __launch_bounds__(kCoefThreads) pair_coef_kernel(const double* __restrict__ w, const double* __restrict__ y,
+                                                                 int64_t n, int64_t npad, int power,
+                                                                 const unsigned long long* wmax, float* __restrict__ sc,
+                                                                 float* __restrict__ c1, float* __restrict__ cy,
+                                                                 double* __restrict__ s0blocks) {
+  const double wscale = ldexp(1.0, -weight_exponent(wmax));      // exact power of two
+  double s0 = 0.0, swy = 0.0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < npad; i += int64_t(gridDim.x) * blockDim.x) {
+    const double pid = (i < n) ? w[i] : 0.0;
+    const double yd = (y && i < n) ? y[i] : 0.0;
+    const double wd = (power == 2) ? pid * pid : pid;
+    const double pis = pid * wscale;                               // normalised weight, <= 1
+    sc[i] = (power == 2) ? float(pis) : float(sqrt(pis));
+    if (c1 != sc) c1[i] = float(pis);
+    if (cy) cy[i] = float(((power == 2) ? pis * pis : pis) * yd);
+    s0 += wd;
+    swy = fma(wd, yd, swy);
+  }
+  __shared__ double red[2][kCoefThreads / 32];
+  s0 = warp_sum(s0);
+  swy = warp_sum(swy);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0;
+    red[1][threadIdx.x >> 5] = swy;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < kCoefThreads / 32; ++k) {
+      a += red[0][k];
+      b += red[1][k];
+    }
+    s0blocks[size_t(blockIdx.x) * 2 + 0] = a;
+    s0blocks[size_t(blockIdx.x) * 2 + 1] = b;
   }
 }
 
@@ -644,10 +626,9 @@ __global__ void __launch_bounds__(256) gram_tf32_pair_finalize_kernel(const Pair
     return;
   }
   const int64_t k = idx - gtotal;
-  if (k < 2) {          // S0, Swy: CTA 0 of the pairs of type 0
+  if (k < 2) {          // S0, Swy: block partials of the coefficient kernel, in block order
     double s = 0.0;
-    for (int sl = pp.first[0]; sl < pp.first[1]; ++sl)
-      for (int t = 0; t < kTeams; ++t) s += p.s0part[((size_t(sl) * 2) * kTeams + t) * 2 + k];
+    for (int b = 0; b < pp.coef_blocks; ++b) s += pp.s0blocks[size_t(b) * 2 + k];
     out[k] = bad ? nan("") : ((k == 1 && !has_y) ? 0.0 : s);
     return;
   }
@@ -660,12 +641,25 @@ __global__ void __launch_bounds__(256) gram_tf32_pair_finalize_kernel(const Pair
     double s = 0.0;
     if (which == 0 || has_y)
       for (int sl = pp.first[type]; sl < pp.first[type + 1]; ++sl)
-        for (int t = 0; t < kTeams; ++t) s += p.spart[(((size_t(sl) * 2 + r) * kTeams + t) * 2 + which) * 128 + fin];
+        for (int t = 0; t < kWorkers; ++t) s += p.spart[(((size_t(sl) * 2 + r) * kWorkers + t) * 2 + which) * 128 + fin];
     out[2 + which * d + f] = bad ? nan("") : s * (which == 0 ? up1 : upw);
   }
 }
 
 }  // namespace
+
+// Scratch the pair path needs for n rows (partials for one CTA per SM + the FP32 row coefficients): asked for by
+// rlvi_weighted_moments_f32 BEFORE it queues the weight-maximum kernel, because the scratch must not move afterwards.
+size_t rlvi_tf32_pair_scratch_bytes(int sm_count, int64_t n, int power, bool has_y) {
+  const size_t grid = size_t(sm_count);
+  const size_t gbytes = grid * 2 * kMB * kMB * sizeof(double);
+  const size_t sbytes = grid * kWorkers * 2 * 128 * sizeof(double);
+  const int64_t npad = (n + kR - 1) / kR * kR;
+  const int ncoef = 1 + (power == 1 ? 1 : 0) + (has_y ? 1 : 0);
+  const size_t cbytes = (size_t(npad) * 4 + 255) / 256 * 256;
+  const size_t s0bytes = (size_t(sm_count) * 8 * 2 * sizeof(double) + 255) / 256 * 256;
+  return 4096 + gbytes + sbytes + s0bytes + cbytes * size_t(ncoef) + 4096;
+}
 
 // Host side of the pair path.  `p` arrives with w, y, n, d, power, box3d, err, wmax filled in by
 // rlvi_weighted_moments_f32 (which also ran the weight-maximum kernel); returns RLVI_ERR_UNSUPPORTED when the shape or
@@ -673,21 +667,24 @@ __global__ void __launch_bounds__(256) gram_tf32_pair_finalize_kernel(const Pair
 int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap3, tf32::Tf32Params p,
                            int precision, int want_gram, double* out, cudaStream_t st) {
   const int nb = (p.d + kMB - 1) / kMB;
-  if (nb != 2 && nb != 4) return RLVI_ERR_UNSUPPORTED;
+  if (nb < 2 || nb > 4) return RLVI_ERR_UNSUPPORTED;     // d <= 128: the single-CTA kernel
   if (getenv("RLVI_TF32_NO_PAIR")) return RLVI_ERR_UNSUPPORTED;
   PairParams pp;
   memset(&pp, 0, sizeof(pp));
-  pp.nbp = nb / 2;
+  pp.nbp = (nb + 1) / 2;                                // d = 257..384: the fourth block is zero-filled by the TMA
   pp.ntypes = (pp.nbp == 1) ? 1 : 3;
 
-  const void* fn;
-  if (precision == RLVI_TF32X1) fn = p.y ? (const void*)gram_tf32_pair_kernel<1, true> : (const void*)gram_tf32_pair_kernel<1, false>;
-  else fn = p.y ? (const void*)gram_tf32_pair_kernel<3, true> : (const void*)gram_tf32_pair_kernel<3, false>;
-  RLVI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-
-  // how many pairs can be resident at once (one CTA per SM, two SMs of a TPC per pair)
-  int max_pairs = 0;
-  {
+  const int variant = (precision == RLVI_TF32X1 ? 0 : 2) + (p.y ? 1 : 0);
+  const void* fns[4] = {(const void*)gram_tf32_pair_kernel<1, false>, (const void*)gram_tf32_pair_kernel<1, true>,
+                        (const void*)gram_tf32_pair_kernel<3, false>, (const void*)gram_tf32_pair_kernel<3, true>};
+  const void* fn = fns[variant];
+  // once per (device, kernel): the shared-memory opt-in and how many pairs can be resident at once (one CTA per SM,
+  // the two SMs of a TPC per pair) -- both are host-side driver calls of ~1 ms
+  static int cached_pairs[64][4];
+  const int dev_slot = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : 0;
+  int max_pairs = cached_pairs[dev_slot][variant];
+  if (max_pairs == 0) {
+    RLVI_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(unsigned(ctx->sm_count / 2 * 2), 1, 1);
@@ -705,6 +702,7 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
       cudaGetLastError();
       max_pairs = ctx->sm_count / 2;
     }
+    cached_pairs[dev_slot][variant] = max_pairs;
   }
   if (max_pairs > ctx->sm_count / 2) max_pairs = ctx->sm_count / 2;
   if (getenv("RLVI_TF32_STATS")) fprintf(stderr, "[tf32 pair] resident pairs: %d\n", max_pairs);
@@ -720,7 +718,8 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   if (pp.ntypes == 1) {
     count[0] = int(ntiles < max_pairs ? ntiles : max_pairs);
   } else {
-    double wdiag = (precision == RLVI_TF32X1) ? 1.0 : 1.0, woff = (precision == RLVI_TF32X1) ? 1.6 : 1.15;
+    // measured per-tile cost (profiles/r02_tf32_pair_stats.txt): the tensor pipe bounds both kinds of pair alike
+    double wdiag = 1.0, woff = 1.0;
     if (const char* e = getenv("RLVI_TF32_PAIR_OFFDIAG")) woff = atof(e);
     int total = max_pairs;
     if (ntiles * 3 < total) total = int(ntiles) * 3;
@@ -740,17 +739,21 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   const int npairs = pp.first[pp.ntypes];
   const int grid = 2 * npairs;
 
-  p.nb = nb;
+  p.nb = 2 * pp.nbp;
   p.ngroups = 0;
   p.nslots = 0;
   p.chunks_per_flush = 256;
   p.window = 0;
-  if (const char* e = getenv("RLVI_TF32_PAIR_DEBUG")) p.window = atoi(e);   // bring-up: 1 no MMA, 2 no transform, 4 no TMEM read, 8 no TMA
   const size_t gbytes = size_t(grid) * 2 * kMB * kMB * sizeof(double);
-  const size_t sbytes = size_t(grid) * kTeams * 2 * 128 * sizeof(double);
-  const size_t s0bytes = size_t(grid) * kTeams * 2 * sizeof(double);
+  const size_t sbytes = size_t(grid) * kWorkers * 2 * 128 * sizeof(double);
+  const int64_t npad = ntiles * kR;
+  const int ncoef = 1 + (p.power == 1 ? 1 : 0) + (p.y ? 1 : 0);
+  const size_t cbytes = (size_t(npad) * 4 + 255) / 256 * 256;
+  int coef_blocks = int((npad + kCoefThreads * 4 - 1) / (kCoefThreads * 4));
+  if (coef_blocks > ctx->sm_count * 8) coef_blocks = ctx->sm_count * 8;
+  const size_t s0bytes = (size_t(coef_blocks) * 2 * sizeof(double) + 255) / 256 * 256;
   void* scratch = nullptr;
-  const int rc = rlvi_scratch(ctx, 4096 + gbytes + sbytes + s0bytes, &scratch);
+  const int rc = rlvi_scratch(ctx, rlvi_tf32_pair_scratch_bytes(ctx->sm_count, p.n, p.power, p.y != nullptr), &scratch);
   if (rc != RLVI_OK) return rc;
   char* base = static_cast<char*>(scratch);
   if (reinterpret_cast<unsigned int*>(base + 2048) != p.err) {
@@ -759,7 +762,19 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   }
   p.gpart64 = reinterpret_cast<double*>(base + 4096);
   p.spart = reinterpret_cast<double*>(base + 4096 + gbytes);
-  p.s0part = reinterpret_cast<double*>(base + 4096 + gbytes + sbytes);
+  p.s0part = nullptr;
+  pp.s0blocks = reinterpret_cast<double*>(base + 4096 + gbytes + sbytes);
+  pp.coef_blocks = coef_blocks;
+  {
+    float* c0 = reinterpret_cast<float*>(base + 4096 + gbytes + sbytes + s0bytes);
+    float* c1 = (p.power == 1) ? reinterpret_cast<float*>(reinterpret_cast<char*>(c0) + cbytes) : c0;
+    float* c2 = p.y ? reinterpret_cast<float*>(reinterpret_cast<char*>(c0) + cbytes * size_t(ncoef - 1)) : nullptr;
+    pp.coef_sc = c0;
+    pp.coef_c1 = c1;
+    pp.coef_cy = c2;
+    pair_coef_kernel<<<coef_blocks, kCoefThreads, 0, st>>>(p.w, p.y, p.n, npad, p.power, p.wmax, c0, c1, c2, pp.s0blocks);
+    RLVI_LAUNCH_CHECK(ctx);
+  }
   p.progress = nullptr;
   p.stats = nullptr;
   if (getenv("RLVI_TF32_STATS")) {
@@ -780,8 +795,8 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
     RLVI_CUDA(cudaStreamSynchronize(st));
     long long* hst = static_cast<long long*>(malloc(size_t(grid) * 128));
     cudaMemcpy(hst, p.stats, size_t(grid) * 128, cudaMemcpyDeviceToHost);
-    const char* names[8] = {"producer wait empty", "team0 wait full", "team0 busy", "mma wait ready", "mma wait tempty",
-                            "mma issue", "team1 drain", "producer total"};
+    const char* names[8] = {"producer wait empty", "worker0 wait full (x6)", "worker0 busy (x6)", "mma wait ready", "mma wait tempty",
+                            "mma issue", "acc warp drain (x8)", "producer total"};
     for (int t = 0; t < pp.ntypes; ++t) {
       const int cnt = pp.first[t + 1] - pp.first[t];
       const double tiles = double(ntiles) / cnt;
@@ -791,20 +806,13 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
           for (int k = 0; k < 8; ++k) acc[k] += double(hst[(size_t(sl) * 2 + r) * 8 + k]) / cnt;
         fprintf(stderr, "[tf32 pair stats] type %d cta %d (%d pairs, %.0f tiles/CTA), cycles per tile:", t, r, cnt, tiles);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[k] / tiles);
-        const char* fine[5] = {"coef+math", "transform", "proxy fence", "syncwarp+arrive", "flush sums"};
-        fprintf(stderr, " | team0:");
-        for (int k = 0; k < 5; ++k) {
-          double a2 = 0;
-          for (int sl = pp.first[t]; sl < pp.first[t + 1]; ++sl) a2 += double(hst[size_t(grid) * 8 + (size_t(sl) * 2 + r) * 8 + k]) / cnt;
-          fprintf(stderr, " %s=%.0f", fine[k], a2 / tiles);
-        }
         fprintf(stderr, "\n");
       }
     }
     free(hst);
     cudaFree(p.stats);
   }
-  const int64_t total = int64_t(nb) * (nb + 1) / 2 * kMB * kMB + 2 + 2 * int64_t(p.d);
+  const int64_t total = int64_t(p.nb) * (p.nb + 1) / 2 * kMB * kMB + 2 + 2 * int64_t(p.d);
   gram_tf32_pair_finalize_kernel<<<int((total + 255) / 256), 256, 0, st>>>(pp, p.y ? 1 : 0, want_gram, out);
   RLVI_LAUNCH_CHECK(ctx);
   return RLVI_OK;

@@ -94,6 +94,32 @@ __device__ __forceinline__ void tma_load_3d_f32(uint32_t dst_smem, const CUtenso
 // round-to-nearest (ties away from zero in magnitude) onto the TF32 grid, on the bit pattern: what cvt.rna.tf32.f32
 // computes, without its NaN/Inf special-casing (Inf stays Inf, NaN stays NaN under the mask)
 __device__ __forceinline__ uint32_t to_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+// Packed FP32 pairs (SASS FMUL2 / FFMA2: two FP32 lanes per issue slot)
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; "
+      "mov.b64 {%0,%1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+// Dekker / Veltkamp split of FP32 onto the TF32 grid with FP32 arithmetic only: hi = the 11 significant bits of z rounded
+// to nearest (C = 2^13 + 1: t = C z, hi = t - (t - z)), lo = z - hi exactly (|lo| <= 2^-11 |z|; the tensor core reads the
+// upper 11 of its <= 13 significant bits).  Three / four packed instructions per TWO elements instead of two / four
+// integer ones per element.
+__device__ __forceinline__ float2 tf32_hi2(float2 z) {
+  const float2 c = make_float2(8193.f, 8193.f), m1 = make_float2(-1.f, -1.f);
+  const float2 t = f2mul(z, c);
+  const float2 u = f2fma(z, m1, t);
+  return f2fma(u, m1, t);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
