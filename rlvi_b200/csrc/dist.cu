@@ -108,8 +108,8 @@ struct StatsParams {
 __global__ void __launch_bounds__(256) stats_allreduce_kernel(const StatsParams p) {
   __shared__ int s_last, s_fail;
   const int parity = int(p.call_index & 1ull);
-  const size_t tag_off = size_t(16) * p.world + size_t(parity) * p.world;
-  const size_t data_off = size_t(18) * p.world + size_t(parity) * p.world * RLVI_DIST_STATS_CAPACITY;
+  const size_t tag_off = size_t(24) * p.world + size_t(parity) * p.world;
+  const size_t data_off = size_t(26) * p.world + size_t(parity) * p.world * RLVI_DIST_STATS_CAPACITY;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   // ---- phase A: my values into slot `rank` of every rank's window (remote stores over NVLink)
   if (e < p.count) {

@@ -13,11 +13,11 @@
 // redundantly by every block from the same bits, in the reference's FP64 operation order, so the
 // loop exits on the device without a host round trip.  A final pass writes pi.
 //
-// Cross-block reduction is deterministic and single-hop: block partials -> the LAST-arriving block
-// sums them in block order and publishes the rank's totals + a sequence tag (to a local window, or
-// with `dist` set to every peer's inbox over NVLink) -> all blocks poll their own window for the tags
-// (which is the grid barrier) and add the `world` slots in rank order, so every block of every rank
-// sees identical totals and takes the same stop decision.
+// Cross-block reduction is deterministic, two hops, no atomics: block partials as self-validating "LL" words ->
+// block 0 sums them in a fixed order and publishes the rank's totals as LL words (to a local window, or with
+// `dist` set to every peer's inbox over NVLink) -> all blocks poll their own window (which is the grid barrier)
+// and add the `world` slots in rank order, so every block of every rank sees identical totals and takes the
+// same stop decision.
 #include <math.h>
 #include <stdlib.h>
 
@@ -43,8 +43,8 @@ struct FpParams {
   int64_t n_global;
   double tol;
   int maxiter;
-  double* partials;       // [2][grid][4]
-  unsigned int* control;  // [0] barrier counter, [1] failure flag
+  double* partials;       // [2][grid][6] LL words (two per double)
+  unsigned int* control;  // [1] failure flag
   rlvi_fp_result* result;
   int rank, world;
   double* inbox;
@@ -90,22 +90,51 @@ struct FpShared {
   double warp_part[3 * (kFpThreads / 32)];
   double total[3];
   int failed;
-  int is_last;
 };
+
+// ---- "LL" words (the idea of NCCL's low-latency protocol): 8 bytes = 32 bits of payload + a 32-bit sequence tag,
+// written with ONE store and read with ONE load, so a word is either old or complete and needs no fence, flag or
+// atomic around it.  A double travels as two words (low half, high half); a reader spins until both carry the tag.
+__device__ __forceinline__ void st_ll(unsigned long long* p, double v, unsigned int tag, bool sys) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (b >> 32) | ((unsigned long long)tag << 32);
+  if (sys) asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+  else asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+// true when both words of the double at p carry `tag`
+__device__ __forceinline__ bool ld_ll(const unsigned long long* p, unsigned int tag, bool sys, double& v) {
+  unsigned long long w0, w1;
+  if (sys) asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return (unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag;
+}
 
 // Grid-wide (and, with dist, cross-GPU) reduction of three values; v2 uses OP2.  On return all threads
 // of all blocks (of all ranks) hold the same totals.  `round` counts reduction rounds and is advanced here.
 // Returns false if a wait timed out (a peer died / launch was not co-resident).
 //
-// One hop: every block stores its partial and takes a ticket; the LAST block to arrive sums the partials in
-// block order and PUBLISHES the rank's totals + a sequence tag -- into slot `rank` of every rank's window
-// (over NVLink for the peers; world == 1 uses a local window in the context scratch).  All blocks then poll
-// their own window for the `world` tags, which doubles as the grid barrier, and add the slots in rank order.
-template <typename T, int OP2>
+// Two hops, no atomics, no fences on the critical path: every block stores its partial as LL words; BLOCK 0 of the rank
+// gathers them (all its threads poll, block j by thread j mod 256; fixed summation order) and stores the rank's totals
+// as LL words into slot `rank` of every rank's window (over NVLink for the peers; world == 1 uses a local window in
+// the context scratch); every block then polls its own window for the `world` totals -- which is also the grid
+// barrier -- and adds them in rank order, so all blocks of all ranks hold the same bits.  (Round 1 of the build passed
+// through the last-arriving block with a ticket atomic, __threadfence and a release/acquire flag.)
+// PUBLISH: the reduction must also make the blocks' earlier global writes visible to each other (pass 1 of the
+// fixed point writes e[], which the bulk-copy ring of other warps reads later): one fence on each side.
+template <typename T, int OP2, bool PUBLISH>
 __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, double& v1, double& v2,
                                 unsigned int& round) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = kFpThreads / 32;
+  const bool sys = p.world > 1;
+  const unsigned int buf = round & 1u;
+  const unsigned int tag = (unsigned int)((p.call_index << 12) + round + 1ull);     // never 0: round + 1 in [1, 4096)
+  unsigned long long* part = reinterpret_cast<unsigned long long*>(p.partials) + size_t(buf) * gridDim.x * 6;
+  // window slot: two per call parity and two per round parity, so a fast rank that already started the NEXT round / call
+  // can never overwrite a slot a slow rank has not read yet (a rank is at most one published round ahead of any peer)
+  const size_t slot = (size_t(((p.call_index & 1ull) << 1) | buf) * p.world) * 6;
   // ---- block stage: fixed xor tree per warp, then warp partials in warp order
   v0 = warp_sum(v0);
   v1 = warp_sum(v1);
@@ -116,9 +145,8 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     sh.warp_part[NW + warp] = v1;
     sh.warp_part[2 * NW + warp] = v2;
   }
+  if (threadIdx.x == 0) sh.failed = 0;
   __syncthreads();
-  const unsigned int buf = round & 1u;
-  double* mine = p.partials + (size_t(buf) * gridDim.x + blockIdx.x) * 4;
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0, c = sh.warp_part[2 * NW];
     for (int w = 0; w < NW; ++w) {
@@ -127,65 +155,85 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
       const double t = sh.warp_part[2 * NW + w];
       c = (OP2 == OP_SUM) ? (w == 0 ? t : c + t) : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
     }
-    mine[0] = a;
-    mine[1] = b;
-    mine[2] = c;
-    __threadfence();
-    const unsigned int ticket = atomicAdd(p.control, 1u);
-    sh.is_last = (ticket == (round + 1u) * gridDim.x - 1u) ? 1 : 0;
-    if (sh.is_last) __threadfence();
+    if (PUBLISH) __threadfence();        // this block's global writes (ordered before by the barrier) first
+    unsigned long long* mine = part + size_t(blockIdx.x) * 6;
+    st_ll(mine + 0, a, tag, false);
+    st_ll(mine + 2, b, tag, false);
+    st_ll(mine + 4, c, tag, false);
   }
-  __syncthreads();
-  // Tag and window slot: two windows per call parity and two per round parity, so a fast rank that already
-  // started the NEXT round / call can never overwrite a slot a slow rank has not read yet (a rank can be at
-  // most one published round ahead of any peer).
-  const unsigned long long tag = (p.call_index << 20) + round + 1ull;
-  const size_t slot = (size_t(((p.call_index & 1ull) << 1) | buf) * p.world) * 4;
-  if (warp == 0) {
-    if (sh.is_last) {
-      // ---- the last block sums all block partials in block order (lane-strided, then xor tree) ...
-      const double* all = p.partials + size_t(buf) * gridDim.x * 4;
-      double a = 0.0, b = 0.0;
-      double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
-      for (unsigned int j = lane; j < gridDim.x; j += 32) {
-        a += ld_volatile_f64(all + j * 4 + 0);
-        b += ld_volatile_f64(all + j * 4 + 1);
-        const double t = ld_volatile_f64(all + j * 4 + 2);
-        c = (OP2 == OP_SUM) ? c + t : (OP2 == OP_MIN ? fmin(c, t) : fmax(c, t));
-      }
-      a = warp_sum(a);
-      b = warp_sum(b);
-      c = (OP2 == OP_SUM) ? warp_sum(c) : (OP2 == OP_MIN ? warp_min(c) : warp_max(c));
-      // ---- ... and publishes them to every rank's window (lane r -> rank r)
-      if (lane < p.world) {
-        double* dst = (p.world > 1 ? p.peer_inbox[lane] : p.inbox) + slot + size_t(p.rank) * 4;
-        dst[0] = a;
-        dst[1] = b;
-        dst[2] = c;
-        if (p.world > 1) {      // peers read it over NVLink: system scope
-          __threadfence_system();
-          st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
-        } else {                // single GPU: device scope is enough (and cheaper)
-          st_release_gpu_u64(reinterpret_cast<unsigned long long*>(dst + 3), tag);
+  if (blockIdx.x == 0) {
+    // ---- block 0 gathers the block partials (thread t: blocks t, t + 256, ...) and sums them in a fixed order
+    double a = 0.0, b = 0.0;
+    double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
+    int failed = 0;
+    for (unsigned int j = threadIdx.x; j < gridDim.x && !failed; j += kFpThreads) {
+      const unsigned long long* src = part + size_t(j) * 6;
+      double x0, x1, x2;
+      const unsigned long long t0 = gtime_ns();
+      unsigned int spins = 0;
+      for (;;) {
+        const bool k0 = ld_ll(src + 0, tag, false, x0), k1 = ld_ll(src + 2, tag, false, x1), k2 = ld_ll(src + 4, tag, false, x2);
+        if (k0 && k1 && k2) break;
+        if ((++spins & 63u) == 0u) {
+          if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
+          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
         }
       }
+      if (!failed) {
+        a += x0;
+        b += x1;
+        c = (OP2 == OP_SUM) ? c + x2 : (OP2 == OP_MIN ? fmin(c, x2) : fmax(c, x2));
+      }
     }
-    // ---- every block: wait for the `world` tags in its own window, add the slots in rank order
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = (OP2 == OP_SUM) ? warp_sum(c) : (OP2 == OP_MIN ? warp_min(c) : warp_max(c));
+    if (failed) sh.failed = 1;
+    __syncthreads();                     // warp_part was consumed by thread 0 above
+    if (lane == 0) {
+      sh.warp_part[warp] = a;
+      sh.warp_part[NW + warp] = b;
+      sh.warp_part[2 * NW + warp] = c;
+    }
+    __syncthreads();
+    if (warp == 0 && !sh.failed) {
+      double ta = 0.0, tb = 0.0, tc = sh.warp_part[2 * NW];
+      for (int w = 0; w < NW; ++w) {
+        ta += sh.warp_part[w];
+        tb += sh.warp_part[NW + w];
+        const double t = sh.warp_part[2 * NW + w];
+        tc = (OP2 == OP_SUM) ? (w == 0 ? t : tc + t) : (OP2 == OP_MIN ? fmin(tc, t) : fmax(tc, t));
+      }
+      // ---- ... and publishes the rank's totals to every rank's window (lane r -> rank r)
+      if (PUBLISH) __threadfence();
+      for (int r = lane; r < p.world; r += 32) {
+        unsigned long long* dst =
+            reinterpret_cast<unsigned long long*>(p.world > 1 ? p.peer_inbox[r] : p.inbox) + slot + size_t(p.rank) * 6;
+        st_ll(dst + 0, ta, tag, sys);
+        st_ll(dst + 2, tb, tag, sys);
+        st_ll(dst + 4, tc, tag, sys);
+      }
+    }
+  }
+  if (warp == 0) {
+    // ---- every block: wait for the `world` totals in its own window, add them in rank order
     double ra = 0.0, rb = 0.0, rc = 0.0;
     int failed = 0;
     if (lane < p.world) {
-      const double* src = p.inbox + slot + size_t(lane) * 4;
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.inbox) + slot + size_t(lane) * 6;
       const unsigned long long t0 = gtime_ns();
-      const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 3);
-      while ((p.world > 1 ? ld_acquire_sys_u64(flag) : ld_acquire_gpu_u64(flag)) != tag) {
-        if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
-        if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+      unsigned int spins = 0;
+      for (;;) {
+        const bool k0 = ld_ll(src + 0, tag, sys, ra), k1 = ld_ll(src + 2, tag, sys, rb), k2 = ld_ll(src + 4, tag, sys, rc);
+        if (k0 && k1 && k2) break;
+        if ((++spins & 63u) == 0u) {
+          if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
+          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+        }
       }
-      ra = ld_volatile_f64(src + 0);
-      rb = ld_volatile_f64(src + 1);
-      rc = ld_volatile_f64(src + 2);
     }
     failed = __any_sync(0xffffffffu, failed);
+    if (PUBLISH) __threadfence();        // acquire side: the other blocks' writes are visible to this block from here on
     double a = 0.0, b = 0.0;
     double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
     for (int r = 0; r < p.world; ++r) {      // rank-ordered sequential sum (world <= 32), same bits everywhere
@@ -198,7 +246,7 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
       sh.total[0] = a;
       sh.total[1] = b;
       sh.total[2] = c;
-      sh.failed = failed;
+      if (failed) sh.failed = 1;
     }
   }
   __syncthreads();
@@ -707,11 +755,11 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
       // ring mode reads e[] with the TMA engine (async proxy) in the later passes: order this thread's generic
       // stores of e before them (the grid barrier below then publishes them to the other CTAs)
       if (ec.ring && have_losses) asm volatile("fence.proxy.async;" ::: "memory");
-      ok = grid_allreduce3<double, OP_MAX>(p, sh, s1, s2, mx, round);
+      ok = grid_allreduce3<double, OP_MAX, true>(p, sh, s1, s2, mx, round);
       emax = mx;
     } else {
       double z = 0.0;
-      ok = grid_allreduce3<double, OP_SUM>(p, sh, s1, s2, z, round);
+      ok = grid_allreduce3<double, OP_SUM, false>(p, sh, s1, s2, z, round);
     }
     if (!ok) break;
     S = s1;
@@ -792,7 +840,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_deep_f32(const FpParams<
 #pragma unroll
     for (int j = 0; j < W; ++j) mn = fmin(mn, double(rv[j]));
   });
-  ok = grid_allreduce3<float, OP_MIN>(p, sh, z0, z1, mn, round);
+  ok = grid_allreduce3<float, OP_MIN, true>(p, sh, z0, z1, mn, round);
   const float rmin = float(mn);
 
   float rho_new = float(0.95 / (1.0 - 0.95));   // Python-float ratio, cast when it meets the FP32 tensor
@@ -845,11 +893,11 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_deep_f32(const FpParams<
         });
       }
       if (k == 1) {
-        ok = grid_allreduce3<float, OP_MAX>(p, sh, s1, s2, mx, round);
+        ok = grid_allreduce3<float, OP_MAX, true>(p, sh, s1, s2, mx, round);
         emax = mx;
       } else {
         double z = 0.0;
-        ok = grid_allreduce3<float, OP_SUM>(p, sh, s1, s2, z, round);
+        ok = grid_allreduce3<float, OP_SUM, true>(p, sh, s1, s2, z, round);
       }
       if (!ok) break;
       S = s1;
@@ -1083,13 +1131,14 @@ int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStr
   int grid = int(want < 1 ? 1 : (want > max_grid ? max_grid : want));
   void* scratch = nullptr;
   const size_t ctrl = 4096;
-  int rc = rlvi_scratch(ctx, ctrl + size_t(2) * grid * 4 * sizeof(double), &scratch);
+  const size_t part_bytes = size_t(2) * grid * 6 * sizeof(unsigned long long);   // [2 round parities][grid][3 doubles as LL words]
+  int rc = rlvi_scratch(ctx, ctrl + part_bytes, &scratch);
   if (rc != RLVI_OK) return rc;
   p.control = reinterpret_cast<unsigned int*>(scratch);
   p.partials = reinterpret_cast<double*>(static_cast<char*>(scratch) + ctrl);
-  // [0,64): ticket counter + failure flag; [256,512): the local window used when world == 1 (4 slots x 4
-  // doubles, tags start at 1 so the zeroed window never matches)
-  RLVI_CUDA(cudaMemsetAsync(p.control, 0, 512, stream));
+  // [0,64): failure flag; [256, 256 + 192): the local window used when world == 1 (4 slots x 6 LL words); then the block
+  // partials.  All zeroed: LL tags start at 1, so a zeroed (or any earlier call's) word never matches.
+  RLVI_CUDA(cudaMemsetAsync(p.control, 0, ctrl + part_bytes, stream));
   if (p.world == 1) p.inbox = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
   void* args[] = {&p};
   RLVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kFpThreads), args,
@@ -1109,6 +1158,7 @@ int fill_dist(FpParams<T>& p, const rlvi_fp_dist* dist, int64_t n) {
   if (dist && dist->world > 1) {
     RLVI_REQUIRE(dist->world <= 32 && dist->rank >= 0 && dist->rank < dist->world, "bad rank/world");
     RLVI_REQUIRE(dist->inbox && dist->peer_inbox && dist->n_global >= n, "incomplete rlvi_fp_dist");
+    RLVI_REQUIRE(p.maxiter < 4000, "sharded fixed point: maxiter must be below 4000 (sequence tags of the peer windows)");
     p.rank = dist->rank;
     p.world = dist->world;
     p.n_global = dist->n_global;
@@ -1123,10 +1173,10 @@ int fill_dist(FpParams<T>& p, const rlvi_fp_dist* dist, int64_t n) {
 
 }  // namespace
 
-// window layout (doubles): [0, 16 world) fixed-point slots | [16 world, 18 world) statistics tags (2 parities) |
-// then 2 parities x world x RLVI_DIST_STATS_CAPACITY statistics slots (dist.cu)
+// window layout (doubles): [0, 24 world) fixed-point slots (4 x world x 6 LL words) | [24 world, 26 world) statistics tags
+// (2 parities) | then 2 parities x world x RLVI_DIST_STATS_CAPACITY statistics slots (dist.cu)
 extern "C" int rlvi_fp_dist_inbox_doubles(int world) {
-  return 16 * world + 2 * world + 2 * world * RLVI_DIST_STATS_CAPACITY;
+  return 24 * world + 2 * world + 2 * world * RLVI_DIST_STATS_CAPACITY;
 }
 
 static int fixed_point_f64_impl(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,

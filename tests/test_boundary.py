@@ -48,7 +48,7 @@ def test_library_loads_and_host_only_calls_work(built):
     lib = _lib.load()
     assert lib.rlvi_version() == 100
     assert lib.rlvi_moments_out_doubles(64) == 2 + 2 * 64 + 64 * 64
-    assert lib.rlvi_fp_dist_inbox_doubles(8) == 16 * 8 + 2 * 8 + 2 * 8 * 8192   # fp slots + stats tags + stats slots
+    assert lib.rlvi_fp_dist_inbox_doubles(8) == 24 * 8 + 2 * 8 + 2 * 8 * 8192   # fp slots + stats tags + stats slots
     assert isinstance(lib.rlvi_last_error(), bytes)
 
 
