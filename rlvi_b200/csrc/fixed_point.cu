@@ -403,13 +403,25 @@ __device__ __forceinline__ void trip_fast(const double2 (&v)[kFpUnroll], double 
     one(v[u].y, t1b, q2b);
   }
 }
+// STANDARD only: the trip WITHOUT the stop-test sum -- sum pi' alone, pi' = e / (rho' + e): 5 FP64 instructions per
+// sample instead of 10.  Used for the passes whose stop test is decided by the bound of fp_kernel_f64 (see there).
+__device__ __forceinline__ void trip_sum_only(const double2 (&v)[kFpUnroll], double rho_new, double& t1a, double& t1b) {
+#pragma unroll
+  for (int u = 0; u < kFpUnroll; ++u) {
+    t1a = fma(v[u].x, rcp_fast(rho_new + v[u].x), t1a);
+    t1b = fma(v[u].y, rcp_fast(rho_new + v[u].y), t1b);
+  }
+}
 __device__ __forceinline__ bool finite_f64(double x) {
   return (((unsigned int)__double2hiint(x) >> 20) & 0x7ffu) != 0x7ffu;
 }
 
-template <int VARIANT>
+// SUM_ONLY (STANDARD): accumulate sum pi' only (s2 comes back 0); the IEEE / remainder paths still form (pi' - pi)^2 but
+// their sum is discarded.
+template <int VARIANT, bool SUM_ONLY>
 __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int64_t n, double rho_new,
                                                 double rho_old, double& s1, double& s2) {
+  static_assert(!SUM_ONLY || VARIANT == RLVI_FP_STANDARD, "the sum-only pass exists for the STANDARD variant");
   const double2* ev = reinterpret_cast<const double2*>(e);
   const int64_t nvec = n >> 1;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -454,7 +466,8 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
       for (int u = 0; u < kFpUnroll; ++u) v[u] = ringw[rd * kWarpTrip + u * 32 + lane];
       __syncwarp();                              // every lane has its data: the slot may be re-armed next trip
       double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
-      trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+      if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
+      else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
       if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
         s1a += t1a;
         s1b += t1b;
@@ -477,22 +490,34 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
       wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
     }
     ec.phase = phase;
-    // remainder of the warp's segment (< one trip): one predicated batch of direct loads
+    // remainder of the warp's segment (< one trip): one predicated batch of direct loads, zero-filled (e = 0 adds
+    // nothing to either sum), through the same fast trip -- the IEEE divisions cost ~5x as much per sample
     {
       const int64_t r0 = lo + ntrips * kWarpTrip + lane;
       double2 v[kFpUnroll];
 #pragma unroll
       for (int u = 0; u < kFpUnroll; ++u) v[u] = (r0 + u * 32 < hi) ? ld_e2(ev + r0 + u * 32) : make_double2(0.0, 0.0);
-#pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) {
-        if (r0 + u * 32 < hi) {
-          double pn, d;
-          post_pair_f64<VARIANT>(v[u].x, rho_new, rho_old, pn, d);
-          s1a += pn;
-          s2a = fma(d, d, s2a);
-          post_pair_f64<VARIANT>(v[u].y, rho_new, rho_old, pn, d);
-          s1b += pn;
-          s2b = fma(d, d, s2b);
+      double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
+      if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
+      else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+      if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
+        s1a += t1a;
+        s1b += t1b;
+        q2sa += q2a;
+        q2sb += q2b;
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < kFpUnroll; ++u) {
+          if (r0 + u * 32 < hi) {
+            const double2 w = ld_e2(ev + r0 + u * 32);
+            double pn, d;
+            post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
+            s1a += pn;
+            s2a = fma(d, d, s2a);
+            post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
+            s1b += pn;
+            s2b = fma(d, d, s2b);
+          }
         }
       }
     }
@@ -508,7 +533,8 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
       for (int u = 0; u < kFpUnroll; ++u) v[u] = ld_e2(ev + c + u * stride);
     }
     double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
-    trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+    if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
+    else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
     if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
       s1a += t1a;
       s1b += t1b;
@@ -530,23 +556,36 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
   }
   if (c < nvec) {
     // remainder: ONE predicated trip with all loads in flight together (a chunk-at-a-time tail loop costs a
-    // full memory latency per chunk, which dominated the pass once a shard is L2 resident)
+    // full memory latency per chunk, which dominated the pass once a shard is L2 resident), zero-filled and pushed
+    // through the same fast trip as the full ones (e = 0 adds nothing to either sum; at 2^23 samples per GPU the
+    // remainder is 1 of 7 trips, and with the IEEE divisions it cost more than the other six together)
     double2 v[kFpUnroll];
 #pragma unroll
     for (int u = 0; u < kFpUnroll; ++u) {
       const int64_t i = c + u * stride;
       v[u] = (i < nvec) ? ld_e2c(ec, slot0 + u, ev + i) : make_double2(0.0, 0.0);
     }
-#pragma unroll
-    for (int u = 0; u < kFpUnroll; ++u) {
-      if (c + u * stride < nvec) {
-        double pn, d;
-        post_pair_f64<VARIANT>(v[u].x, rho_new, rho_old, pn, d);
-        s1a += pn;
-        s2a = fma(d, d, s2a);
-        post_pair_f64<VARIANT>(v[u].y, rho_new, rho_old, pn, d);
-        s1b += pn;
-        s2b = fma(d, d, s2b);
+    double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
+    if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
+    else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
+    if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
+      s1a += t1a;
+      s1b += t1b;
+      q2sa += q2a;
+      q2sb += q2b;
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < kFpUnroll; ++u) {
+        if (c + u * stride < nvec) {
+          const double2 w = ld_e2c(ec, slot0 + u, ev + c + u * stride);
+          double pn, d;
+          post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
+          s1a += pn;
+          s2a = fma(d, d, s2a);
+          post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
+          s1b += pn;
+          s2b = fma(d, d, s2b);
+        }
       }
     }
   }
@@ -557,7 +596,7 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
     s2a = fma(d, d, s2a);
   }
   s1 = s1a + s1b;
-  s2 = (s2a + s2b) + ((VARIANT == RLVI_FP_STANDARD) ? (drho * drho) * (q2sa + q2sb) : (q2sa + q2sb));
+  s2 = SUM_ONLY ? 0.0 : (s2a + s2b) + ((VARIANT == RLVI_FP_STANDARD) ? (drho * drho) * (q2sa + q2sb) : (q2sa + q2sb));
 }
 
 // Pass 1 over a precomputed, 16-byte aligned e[] (the loss kernel wrote it): pi' against the constant
@@ -698,11 +737,14 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
     rho_new = pi0 / (1.0 - pi0);
   }
 
-  double S = 0.0, E = 0.0, emax = 0.0, err = 0.0;
+  double S = n_glob * pi0, E = 0.0, emax = 0.0, err = 0.0;
+  const double sqrt_n = sqrt(n_glob);
+  double bound_prev = 0.0, bound_prev2 = 0.0;
   int k = 1, converged = 0;
   bool ok = true;
   for (;; ++k) {
     double s1 = 0.0, s2 = 0.0, mx = 0.0;
+    bool sum_only = false;
     if (k == 1 && VEC && !have_losses) {
       first_pass_vec<VARIANT>(e, ec, p.n, rho_new, pi0, s1, s2, mx);
     } else if (k == 1) {
@@ -734,7 +776,15 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
         }
       });
     } else if (VEC) {
-      stream_pass_vec<VARIANT>(e, ec, p.n, rho_new, rho_old, s1, s2);
+      // Which trip?  By Cauchy-Schwarz  ||pi' - pi||_2 >= |sum pi' - sum pi| / sqrt(N): when that lower bound is above tol
+      // the stop test `err < tol` (rlvi.py:18) is decided WITHOUT the sum of squared differences, and the pass needs
+      // half the FP64 instructions.  The bound is predicted from the last two (it decays geometrically: in the
+      // collapse regime it is within 10 % of err itself, so all passes but the last qualify); a pass that was run
+      // sum-only and whose bound then fails to prove anything is repeated in full, so every decision is the exact one.
+      sum_only = (VARIANT == RLVI_FP_STANDARD) && k < p.maxiter && bound_prev2 > 0.0 &&
+                 bound_prev * fmin(1.0, bound_prev / bound_prev2) > 2.0 * p.tol;
+      if (sum_only) stream_pass_vec<VARIANT, VARIANT == RLVI_FP_STANDARD>(e, ec, p.n, rho_new, rho_old, s1, s2);
+      else stream_pass_vec<VARIANT, false>(e, ec, p.n, rho_new, rho_old, s1, s2);
     } else {
       for_each_chunk<double, VEC>(p.n, [&](int64_t c, int) {
         const int64_t i = c * W;
@@ -762,10 +812,28 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
       ok = grid_allreduce3<double, OP_SUM, false>(p, sh, s1, s2, z, round);
     }
     if (!ok) break;
+    const double bound = fabs(s1 - S) / sqrt_n;          // S still holds the previous pass's sum (N pi0 before pass 1)
+    if (sum_only && !(bound > p.tol * (1.0 + 1e-6))) {
+      // the bound proves nothing this time: repeat the pass with the full trip (all blocks of all ranks hold the
+      // same `bound` bits and come here together)
+      sum_only = false;
+      s1 = 0.0;
+      s2 = 0.0;
+      double z = 0.0;
+      stream_pass_vec<VARIANT, false>(e, ec, p.n, rho_new, rho_old, s1, s2);
+      ok = grid_allreduce3<double, OP_SUM, false>(p, sh, s1, s2, z, round);
+      if (!ok) break;
+    }
+    bound_prev2 = bound_prev;
+    bound_prev = bound;
     S = s1;
-    E = s2;
-    err = sqrt(E);
-    if (err < p.tol) { converged = 1; break; }   // rlvi.py:18 / online main.py:54
+    if (sum_only) {
+      err = bound;                                       // a lower bound of the true error, already above tol
+    } else {
+      E = s2;
+      err = sqrt(E);
+      if (err < p.tol) { converged = 1; break; }   // rlvi.py:18 / online main.py:54
+    }
     if (k >= p.maxiter) break;
     // next pass's ratio from the mean of the posteriors just computed
     rho_old = rho_new;
