@@ -107,6 +107,34 @@ def test_update_weights_tol_maxiter_negative_losses(dev):
     assert r["iters"] == int(g["maxiter"]) and r["converged"] == 0
 
 
+@pytest.mark.parametrize("regime", ["collapse", "clean", "bimodal", "balanced"])
+@pytest.mark.parametrize("tol", [1e-1, 1e-3, 1e-6])
+def test_fixed_point_stop_decision_across_regimes(dev, regime, tol):
+    """fixed_point.cu decides most stop tests of the persistent kernel from the bound |sum pi' - sum pi| / sqrt(N) <= err
+    (sum-only passes) and repeats a pass in full when the bound proves nothing: the iteration count, eps and the
+    reported err must be the oracle's in every regime -- the collapse regime where the bound is tight (rlvi.py:8-20 with
+    mostly large losses), clean data where pi stays near 1, a bimodal loss vector, and one whose posteriors move in
+    opposite directions so that sum pi barely changes while err is large (the bound is useless there)."""
+    from rlvi_b200 import ops
+    rng = np.random.default_rng(11)
+    n = 200001
+    if regime == "collapse":
+        losses = 0.5 * rng.chisquare(4, size=n) + 2.0
+    elif regime == "clean":
+        losses = 0.02 * rng.chisquare(1, size=n) - 3.0
+    elif regime == "bimodal":
+        losses = np.where(rng.random(n) < 0.3, 6.0 + rng.normal(size=n), -1.0 + 0.3 * rng.normal(size=n))
+    else:
+        losses = np.where(np.arange(n) % 2 == 0, -2.9444, 2.9444) + 1e-3 * rng.normal(size=n)   # pi ~ 0.95 / 0.05 around eps ~ 0.5
+    ref, eps, k, err = rlvi_np.fixed_point_trace(losses, tol=tol, maxiter=100)
+    pi, res = ops.fixed_point(cu(losses, dev), tol=tol, maxiter=100)
+    r = ops.read_result(res)
+    assert r["iters"] == k
+    assert abs(r["eps"] - eps) <= F64_TOL * abs(eps)
+    assert abs(r["err"] - err) <= 1e-6 * err + 1e-15
+    assert relmax(pi.cpu().numpy(), ref) < pi_tol(ref)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 1023, 1025, 300001])
 def test_fixed_point_ragged_and_unaligned(dev, n):
     from rlvi_b200 import ops
