@@ -250,6 +250,17 @@ int rlvi_irls_weights_f64(rlvi_ctx* ctx, const double* e, const double* weights,
 int rlvi_rrm_sum_f64(rlvi_ctx* ctx, const double* losses, int64_t n, double inv_alpha, double cutoff, double norm,
                      double* w_out, double* out_sum, void* stream);
 
+/* standard-learning/sever.py:22-31 (linear regression) / :95-104 (PCA): the two per-sample passes of one SEVER filter
+ * step on row-major FP64 X, dot_i = x_i . u (u = device double[d]):
+ *   op 0: c_i = scalar * (dot_i - b_i)  (b may be NULL = 0);  out0_i = c_i, out1_i = active_i * c_i^2,
+ *         out2_i = c_i != 0 ? 1 / c_i : 0   -- the per-sample gradient is g_i = c_i x_i, and
+ *         rlvi_weighted_moments_f64(X, y = out2, weights = out1) then returns sum_active g_i g_i^T and sum_active g_i;
+ *   op 1: out0_i = active_i != 0 ? (a_i * dot_i - scalar)^2 : -1     -- the outlier scores tau_i with a = c, u = v,
+ *         scalar = mean(g) . v.   `active` (0/1 doubles, NULL = all active) is the filter's current active set. */
+int rlvi_sever_pass_f64(rlvi_ctx* ctx, const double* X, int64_t n, int d, const double* u, int op, double scalar,
+                        const double* a, const double* b, const double* active, double* out0, double* out1, double* out2,
+                        void* stream);
+
 /* ---- deep path (FP32) ------------------------------------------------------------------------- */
 /* methods/train_rlvi.py:89-94 fused with its autograd backward (line 96):
  *   loss_i = CE(logits_i, label_i);  residuals[indexes_i] = loss_i (detached: quirk Q8);

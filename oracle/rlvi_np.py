@@ -325,6 +325,45 @@ def rrm_linear_regression(X, y, eps, maxiter=100, tol=1e-3):
     return theta
 
 
+def sever_filter_scores(Xs, c, as_written=True):
+    """standard-learning/sever.py:22-31 / :95-104: gradients g_i = c_i x_i, centred; "top right singular vector"; scores.
+
+    `as_written=True` restates line 26-27 literally: `V = np.linalg.svd(G_cen)[-1]; v = V[:, 0]`.  NumPy returns V^H, whose
+    ROWS are the right singular vectors, so `V[:, 0]` is the vector of FIRST COMPONENTS of all d singular vectors (quirk
+    Q12), and it depends on the sign LAPACK happens to give each of them.  `as_written=False` takes the top right singular
+    vector the comment (and the SEVER paper) mean, `V[0, :]`, which is defined up to a sign the squared score removes."""
+    G_uncen = c[:, None] * Xs
+    G_cen = G_uncen - np.mean(G_uncen, axis=0)
+    Vh = np.linalg.svd(G_cen)[-1]
+    v = Vh[:, 0] if as_written else Vh[0, :]
+    return (G_cen @ v) ** 2
+
+
+def sever_linear_regression(X, y, eps, numiter=4, as_written=True):
+    """standard-learning/sever.py:11-42."""
+    Xs, ys = X, y
+    theta = None
+    for _ in range(numiter):
+        theta = _lstsq(Xs, ys)[0]
+        tau = sever_filter_scores(Xs, 2 * (Xs @ theta - ys), as_written)
+        p = int(eps / 2 * Xs.shape[0])
+        s = np.argsort(-tau)[p:]
+        Xs, ys = Xs[s, :], ys[s]
+    return theta
+
+
+def sever_pca(samples, eps, numiter=4, theta_init=None, as_written=True):
+    """standard-learning/sever.py:82-113 (base learner utils.pca with unit weights = pca_direction)."""
+    Xs = samples
+    theta = None
+    for k in range(numiter):
+        theta = theta_init if (theta_init is not None and k == 0) else pca_direction(Xs, np.ones(len(Xs)))
+        tau = sever_filter_scores(Xs, -2 * (Xs @ theta), as_written)
+        p = int(eps / 2 * Xs.shape[0])
+        Xs = Xs[np.argsort(-tau)[p:], :]
+    return theta
+
+
 # --------------------------------------------------------------------------------------------------
 # The benchmark's unit of work: one E+M step of the logistic model (SURVEY.md section 8d)
 # --------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ SYMBOLS = (
     "rlvi_fixed_point_deep_f32", "rlvi_shift_sum_f64", "rlvi_shift_sum_e_f64", "rlvi_loss_f64", "rlvi_moments_out_doubles",
     "rlvi_weighted_moments_f64", "rlvi_weighted_moments_centered_f64", "rlvi_logistic_grad_f64", "rlvi_wce_fwd_bwd_f32", "rlvi_fn_threshold_f32",
     "rlvi_em_step_logistic_host", "rlvi_dist_window_create", "rlvi_dist_window_open", "rlvi_dist_window_close",
-    "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded", "rlvi_weighted_moments_f32", "rlvi_loss_f32", "rlvi_sigmoid_f64", "rlvi_online_ce_f64", "rlvi_irls_weights_f64", "rlvi_rrm_sum_f64",
+    "rlvi_stats_allreduce_f64", "rlvi_em_step_logistic_host_sharded", "rlvi_weighted_moments_f32", "rlvi_loss_f32", "rlvi_sigmoid_f64", "rlvi_online_ce_f64", "rlvi_irls_weights_f64", "rlvi_rrm_sum_f64", "rlvi_sever_pass_f64",
 )
 
 FP_STANDARD, FP_ONLINE, FP_DEEP = 0, 1, 2
@@ -80,6 +80,7 @@ def load():
         lib.rlvi_online_ce_f64.argtypes = [vp, vp, vp, i64, vp, vp]
         lib.rlvi_irls_weights_f64.argtypes = [vp, vp, vp, i64, vp, vp]
         lib.rlvi_rrm_sum_f64.argtypes = [vp, vp, i64, f64, f64, f64, vp, vp, vp]
+        lib.rlvi_sever_pass_f64.argtypes = [vp, vp, i64, i32, vp, i32, f64, vp, vp, vp, vp, vp, vp, vp]
         lib.rlvi_logistic_grad_f64.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
         lib.rlvi_wce_fwd_bwd_f32.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp]
         lib.rlvi_fn_threshold_f32.argtypes = [vp, vp, i64, f32, f32, i32, vp, vp]

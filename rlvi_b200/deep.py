@@ -17,7 +17,7 @@ import torch
 from . import ops
 
 __all__ = ["train_rlvi", "update_sample_weights", "false_negative_criterion", "weighted_cross_entropy",
-           "selection_mask"]
+           "selection_mask", "GraphedBatchStep"]
 
 
 @torch.no_grad()
@@ -70,9 +70,70 @@ def weighted_cross_entropy(logits, labels, indexes, weights, residuals):
     return _WeightedCE.apply(logits, labels, indexes, weights, residuals)
 
 
-def train_rlvi(train_loader, model, optimizer, residuals, weights, overfit, threshold):
+class GraphedBatchStep:
+    """The per-batch body of train_rlvi.py:84-97 -- model forward, fused weighted cross-entropy (residual scatter, weight
+    gather, accuracy counts), backward, optimizer step -- captured ONCE as a CUDA graph for one batch shape and replayed
+    per batch: a single graph launch instead of the model's and the optimizer's individual launches (SURVEY.md section 8f
+    rank 3).  `optimizer` must be capturable (torch.optim.SGD, or Adam(..., capturable=True) -- the reference's Adam of
+    deep-learning/main.py:263 with that flag).  The warm-up iterations torch needs before a capture run on the given
+    batch and are undone (model, optimizer state and `residuals` are restored), so training is the same as eager."""
+
+    def __init__(self, model, optimizer, residuals, weights, images, labels, indexes, warmup=3):
+        import copy
+
+        self.model, self.optimizer = model, optimizer
+        self.images, self.labels, self.indexes = images.clone(), labels.clone(), indexes.clone()
+        self.stream = torch.cuda.Stream(device=weights.device)
+        saved_model = copy.deepcopy(model.state_dict())
+        saved_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for p, st in optimizer.state.items()}
+        saved_res = residuals.clone()
+        self.stream.wait_stream(torch.cuda.current_stream(weights.device))
+        with torch.cuda.stream(self.stream):          # librlvi_b200 keeps one context per stream: warm it up on this one
+            for _ in range(warmup):
+                optimizer.zero_grad(set_to_none=True)
+                loss, _ = weighted_cross_entropy(model(self.images), self.labels, self.indexes, weights, residuals)
+                loss.backward()
+                optimizer.step()
+            # undo the warm-up IN PLACE: the optimizer's state tensors must exist before the capture (state created inside
+            # it would be re-initialised by every replay), so they are kept and reset to what they held before
+            model.load_state_dict(saved_model)
+            for prm, st in optimizer.state.items():
+                old = saved_opt.get(prm, {})
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()
+                    elif k in old:
+                        st[k] = old[k]
+            residuals.copy_(saved_res)
+        torch.cuda.current_stream(weights.device).wait_stream(self.stream)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.loss, self.correct = weighted_cross_entropy(model(self.images), self.labels, self.indexes, weights,
+                                                             residuals)
+            self.loss.backward()
+            optimizer.step()
+
+    def matches(self, images, labels):
+        return images.shape == self.images.shape and images.dtype == self.images.dtype and labels.shape == self.labels.shape
+
+    def __call__(self, images, labels, indexes):
+        """One training step on this batch; returns (loss, correct) -- tensors the NEXT call overwrites."""
+        self.images.copy_(images, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.indexes.copy_(indexes, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.correct
+
+
+def train_rlvi(train_loader, model, optimizer, residuals, weights, overfit, threshold, cuda_graph=None):
     """train_rlvi.py:52-106 -- one epoch.  Same arguments, same in-place updates of `residuals` /
-    `weights`, same return value `(train_acc, threshold)`."""
+    `weights`, same return value `(train_acc, threshold)`.  `cuda_graph` (an extension, default off): a dict the caller
+    keeps across epochs; full-shape batches then run as one replayed CUDA graph (GraphedBatchStep), ragged ones eagerly."""
     device = weights.device
     train_total = 0
     train_correct = torch.zeros((), dtype=torch.float64, device=device)
@@ -82,6 +143,18 @@ def train_rlvi(train_loader, model, optimizer, residuals, weights, overfit, thre
         labels = labels.to(device, non_blocking=True)                   # train_rlvi.py:82
         indexes = torch.as_tensor(indexes).to(device=device, dtype=torch.int64, non_blocking=True)
 
+        step = None
+        if cuda_graph is not None:
+            step = cuda_graph.get("step")
+            if step is None:
+                step = cuda_graph["step"] = GraphedBatchStep(model, optimizer, residuals, weights, images, labels, indexes)
+            if not step.matches(images, labels):
+                step = None
+        if step is not None:
+            _, correct = step(images, labels, indexes)                  # :84-97 as one graph launch
+            train_total += 1
+            train_correct += correct[0] * (100.0 / labels.size(0))
+            continue
         logits = model(images)                                          # train_rlvi.py:84
         loss, correct = weighted_cross_entropy(logits, labels, indexes, weights, residuals)   # :85-94
         train_total += 1

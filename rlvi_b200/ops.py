@@ -350,6 +350,40 @@ def rrm_sum(losses, inv_alpha, cutoff=1e-16, *, norm=0.0, w_out=None, out=None):
     return out
 
 
+def sever_pass(X, u, op, scalar, *, a=None, b=None, active=None, out0=None, out1=None, out2=None):
+    """rlvi_sever_pass_f64 (sever.py:22-31 / :95-104).  op 0: c = scalar (X u - b) -> (c, active c^2, 1/c);
+    op 1: scores (a (X u) - scalar)^2, -1 for inactive rows.  Returns (out0, out1, out2)."""
+    dev = _dev(X)
+    f64 = torch.float64
+    _chk(X, f64, "X")
+    if X.dim() != 2:
+        raise ValueError("X must be [n, d]")
+    n, d = X.shape
+    _len(_chk(u, f64, "u"), d, "u")
+    _len(_chk(a, f64, "a"), n, "a")
+    _len(_chk(b, f64, "b"), n, "b")
+    _len(_chk(active, f64, "active"), n, "active")
+    if op not in (0, 1):
+        raise ValueError("op must be 0 or 1")
+    if op == 1 and a is None:
+        raise ValueError("op 1 needs the coefficients a")
+    if out0 is None:
+        out0 = torch.empty(n, dtype=f64, device=X.device)
+    if op == 0:
+        if out1 is None:
+            out1 = torch.empty(n, dtype=f64, device=X.device)
+        if out2 is None:
+            out2 = torch.empty(n, dtype=f64, device=X.device)
+    for t, name in ((out0, "out0"), (out1, "out1"), (out2, "out2")):
+        _len(_chk(t, f64, name), n, name)
+    _same_device(X, u, a, b, active, out0, out1, out2)
+    ctx = _ctx(dev)
+    rc = ctx.lib.rlvi_sever_pass_f64(ctx.handle, _p(X), n, d, _p(u), int(op), float(scalar), _p(a), _p(b), _p(active),
+                                     _p(out0), _p(out1), _p(out2), _stream(dev))
+    _lib.check(rc, "rlvi_sever_pass_f64")
+    return out0, out1, out2
+
+
 def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=True, want_per_sample=False,
                 want_correct=False):
     """rlvi_wce_fwd_bwd_f32.  Returns dict(loss [1], dlogits | None, per_sample | None, correct | None)."""

@@ -192,6 +192,29 @@ def rrm_sum(losses, inv_alpha, cutoff=1e-16, *, norm=0.0, w_out=None, out=None):
     return out
 
 
+def sever_pass(X, u, op, scalar, *, a=None, b=None, active=None, out0=None, out1=None, out2=None):
+    """rlvi_sever_pass_f64 as include/rlvi_b200.h describes it."""
+    dot = X @ u
+    act = torch.ones_like(dot) if active is None else active
+    if op == 0:
+        c = scalar * (dot - (b if b is not None else 0.0))
+        o0, o1 = c, act * c * c
+        o2 = torch.where(c != 0, 1.0 / c, torch.zeros_like(c))
+    else:
+        t = a * dot - scalar
+        o0, o1, o2 = torch.where(act != 0, t * t, torch.full_like(t, -1.0)), None, None
+    res = []
+    for dst, val in ((out0, o0), (out1, o1), (out2, o2)):
+        if val is None:
+            res.append(dst)
+        elif dst is None:
+            res.append(val.clone())
+        else:
+            dst.copy_(val)
+            res.append(dst)
+    return tuple(res)
+
+
 def wce_fwd_bwd(logits, labels, weights, residuals, *, indexes=None, want_grad=True, want_per_sample=False,
                 want_correct=False):
     b = logits.shape[0]
@@ -236,11 +259,12 @@ def _as_device(a, like=None, dtype=torch.float64):
 
 def install(monkeypatch):
     """Swap the ops entry points and the host<->device glue of the drop-in modules for the doubles above."""
-    from rlvi_b200 import deep, online, rlvi, rrm, utils
+    from rlvi_b200 import deep, online, rlvi, rrm, sever, utils
     for name in ("fixed_point", "fixed_point_deep", "shift_sum", "shift_sum_e", "loss", "weighted_moments",
-                 "logistic_grad", "wce_fwd_bwd", "fn_threshold", "sigmoid", "online_ce", "irls_weights", "rrm_sum"):
+                 "logistic_grad", "wce_fwd_bwd", "fn_threshold", "sigmoid", "online_ce", "irls_weights", "rrm_sum",
+                 "sever_pass"):
         monkeypatch.setattr(ops, name, globals()[name])
-    for mod in (rlvi, utils, online, rrm):
+    for mod in (rlvi, utils, online, rrm, sever):
         monkeypatch.setattr(mod, "as_device", _as_device)
     for mod in (rlvi, utils):
         monkeypatch.setattr(mod, "as_device_x", lambda a, like=None: _as_device(

@@ -210,8 +210,9 @@ def test_deep_and_online_signatures():
     from rlvi_b200 import deep, online
     assert sig(deep.update_sample_weights) == [("residuals", E_), ("weights", E_), ("tol", 1e-3), ("maxiter", 40)]
     assert sig(deep.false_negative_criterion) == [("weights", E_), ("alpha", 0.05)]
-    assert [n for n, _ in sig(deep.train_rlvi)] == ["train_loader", "model", "optimizer", "residuals", "weights",
-                                                    "overfit", "threshold"]
+    assert [n for n, _ in sig(deep.train_rlvi)][:7] == ["train_loader", "model", "optimizer", "residuals", "weights",
+                                                        "overfit", "threshold"]
+    assert sig(deep.train_rlvi)[7:] == [("cuda_graph", None)]      # extension, off by default
     assert sig(online.update_weights_rlvi)[:3] == [("losses", E_), ("tol", 1e-3), ("maxiter", 100)]
     assert sig(online.cross_entropy) == [("log_proba", E_), ("targets", E_)]
 

@@ -27,12 +27,12 @@ def mods(request, monkeypatch):
         from rlvi_b200 import _lib
         _lib.load()
         assert torch.cuda.is_available()
-    from rlvi_b200 import online, rlvi, rrm, utils
+    from rlvi_b200 import online, rlvi, rrm, sever, utils
 
     class NS:
         pass
     ns = NS()
-    ns.rlvi, ns.utils, ns.rrm, ns.online, ns.kind = rlvi, utils, rrm, online, request.param
+    ns.rlvi, ns.utils, ns.rrm, ns.online, ns.sever, ns.kind = rlvi, utils, rrm, online, sever, request.param
     return ns
 
 
@@ -87,6 +87,30 @@ def test_rrm_weights_and_linear_regression(mods):
     assert relmax(mods.rrm.linear_regression(g["X"], g["y"], float(g["eps"])), g["theta"]) < 1e-6
     X, _ = np.split(g["X"], [300], axis=0)
     assert mods.rrm.mean(g["X"], 0.2).shape == (6,)
+
+
+def test_sever_filter(mods):
+    """standard-learning/sever.py:11-42 and :82-113 on the statistics kernels (the active set as a 0/1 weight vector, the top
+    right singular vector of the centred gradients as the top eigenvector of their d x d scatter).  The oracle restates the
+    reference literally and is pinned bit for bit on its goldens; the drop-in implements the algorithm the reference's
+    comment names -- line 27 of the reference takes a COLUMN of NumPy's V^H (quirk Q12, LAPACK-sign dependent, not
+    reproducible without an SVD of the n x d gradient matrix) -- and is compared with the oracle's `as_written=False`."""
+    g = load_golden("sever_linreg_n600_d8")
+    X, y, eps = g["X"], g["y"], float(g["eps"])
+    assert relmax(rlvi_np.sever_linear_regression(X, y, eps), g["theta"]) == 0.0
+    th = mods.sever.linear_regression(X, y, eps)
+    assert isinstance(th, np.ndarray) and relmax(th, rlvi_np.sever_linear_regression(X, y, eps, as_written=False)) < 1e-9
+    g = load_golden("sever_pca_n500_d6")
+    S, eps = g["samples"], float(g["eps"])
+    assert relmax(rlvi_np.sever_pca(S, eps), g["theta"]) == 0.0
+    assert relmax(mods.sever.pca(S, eps), rlvi_np.sever_pca(S, eps, as_written=False)) < 1e-9
+    # theta_init replaces the first base fit only (sever.py:90-91)
+    t0 = np.ones(6) / np.sqrt(6.0)
+    assert relmax(mods.sever.pca(S, 0.3, theta_init=t0), rlvi_np.sever_pca(S, 0.3, theta_init=t0, as_written=False)) < 1e-9
+    # eps small enough that nothing is filtered: the plain least-squares fit
+    g = load_golden("sever_linreg_n600_d8")
+    th = mods.sever.linear_regression(g["X"], g["y"], 1e-4)
+    assert relmax(th, np.linalg.lstsq(g["X"], g["y"], rcond=None)[0]) < 1e-9
 
 
 def test_config1_monte_carlo_replay(mods):
