@@ -37,7 +37,11 @@ def oracle_moments(X32, w, y, power):
 @pytest.mark.parametrize("n,d,power,with_y", [(768, 64, 2, False), (4096, 128, 2, False), (5000, 256, 1, True),
                                               (20000, 512, 2, False), (777, 100, 1, True), (33, 512, 2, False),
                                               (1, 64, 1, False), (17, 4, 1, True), (100000, 384, 1, False),
-                                              (3000, 132, 2, True)])
+                                              (3000, 132, 2, True),
+                                              # CTA-pair kernel edges: partial third / fourth feature block, 2-D boxes
+                                              # (d % 32 != 0), fewer tiles than pairs, y with both powers
+                                              (2049, 260, 1, True), (999, 500, 2, True), (70000, 448, 1, True),
+                                              (40, 256, 2, True)])
 def test_moments_f32_tf32x3_matches_oracle(n, d, power, with_y):
     rng = np.random.default_rng(n + d)
     X = rng.normal(size=(n, d)).astype(np.float32)
