@@ -83,6 +83,19 @@ def timeit(fn, reps=10, warm=3):
     return float(np.median(ts))
 
 
+def tensor_roofline(issued_tflops):
+    """The TF32 Gram against the tensor roofline that applies to it: TF32 runs at half the bf16 rate, and under tensor load
+    the SM clock is power-managed, so the denominator is MEASURED_PEAKS.json's SUSTAINED cuBLAS bf16 figure / 2."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        peaks = json.load(open(path))
+        peak, src = float(peaks["bf16_tflops_sustained"]) / 2.0, "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2)"
+    except Exception:
+        peak, src = 2250.0 / 2.0, "nominal dense bf16 2250 TFLOP/s / 2 (MEASURED_PEAKS.json absent)"
+    return {"bound": "tensor", "kernel": "gram_tf32_pair_kernel<3>", "achieved": issued_tflops, "peak": peak, "unit": "TFLOP/s",
+            "frac": issued_tflops / peak, "peak_source": src}
+
+
 def config3(dev, log2n=24, d=512, seed=3):
     """Config 3 at its named size: one robust-PCA E+M step on FP32-stored X (32 GiB)."""
     n = 1 << log2n
@@ -140,7 +153,11 @@ def config3(dev, log2n=24, d=512, seed=3):
            "fixed_point_ms": t_fp, "gram_tf32x3_ms": t_g3, "gram_tf32x1_ms": t_g1,
            "gram_tf32x3_GBps": n * (d * 4 + 8) / t_g3 / 1e6, "gram_tf32x1_GBps": n * (d * 4 + 8) / t_g1 / 1e6,
            "gram_useful_TFLOPs_x3": n * d * (d + 1) / t_g3 / 1e9, "gram_useful_TFLOPs_x1": n * d * (d + 1) / t_g1 / 1e9,
-           "gram_issued_TFLOPs_x3": 3 * n * d * (d + 128) / t_g3 / 1e9, "gram_issued_TFLOPs_x1": n * d * (d + 128) / t_g1 / 1e9,
+           # issued: the pair kernel computes 12 of the 16 128 x 128 blocks (the 10 of the upper triangle + the redundant
+           # lower block of each diagonal pair), 3 passes for 3xTF32; 2 * rows * 128 * 128 flop per block
+           "gram_issued_TFLOPs_x3": 3 * 12 * 2 * n * 128 * 128 / t_g3 / 1e9 if d == 512 else 3 * n * d * (d + 128) / t_g3 / 1e9,
+           "gram_issued_TFLOPs_x1": 12 * 2 * n * 128 * 128 / t_g1 / 1e9 if d == 512 else n * d * (d + 128) / t_g1 / 1e9,
+           "tensor_roofline_x3": tensor_roofline(3 * 12 * 2 * n * 128 * 128 / t_g3 / 1e9) if d == 512 else None,
            "step_ms_tf32x3": step3, "samples_per_s_tf32x3": n / step3 * 1e3,
            "samples_per_s_tf32x1": n / (t_loss + t_fp + t_g1) * 1e3,
            "hbm_floor_ms_per_X_pass": n * d * 4 / 6538e6,
