@@ -20,14 +20,21 @@
 // (tile t of slot s: s, s + nslots, ...); the off-diagonal type has twice the load / transform work per tile and gets
 // proportionally more pairs.  CTA r of a diagonal pair also owns the column sums of feature block 2 P + r.
 //
-// Per CTA the roles are those of gram_tf32.cu (TMA producer, three transform teams, two of them draining TMEM), with
-// the cross-CTA edges of the protocol:
-//   * transform warps of BOTH CTAs arrive (one elected lane per warp, release.cluster) on the LEADER's `ready` barrier;
-//   * only the leader (cluster rank 0) issues tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster releases
-//     the stage (`empty`) and publishes the chunk (`tfull`) in both CTAs;
-//   * the accumulator warps of both CTAs arrive on the leader's `tempty` after reading their own TMEM back;
-//   * cluster barriers after set-up and before TMEM is freed, and each producer drains its `empty` barriers before
-//     leaving, so no multicast arrive can land in a CTA that has exited.
+// Per CTA, warp-specialised (16 warps; setmaxnreg 96 for warpgroups 0-1, 160 for warpgroups 2-3):
+//   warp 0      TMA producer: per tile ONE 3-D tensor-map box per loaded feature block (32 floats x 16 rows x 4 column
+//               groups) + bulk copies of the tile's FP32 row coefficients (written once per call by pair_coef_kernel: no
+//               FP64 instruction runs in this kernel's inner loops -- FP64 issued while the tensor pipe is busy waits for it);
+//   warp 1      MMA issuer, in the LEADER CTA (cluster rank 0) only: tcgen05.mma.cta_group::2.kind::tf32, then
+//               tcgen05.commit ... multicast::cluster releases the stage (`empty`) and publishes the chunk (`tfull`) in
+//               both CTAs;
+//   warps 2-7   six single-warp TRANSFORM workers, tile t -> worker t mod 6, in place on the landed tile (z = s x split into
+//               TF32 hi + exact remainder lo with packed FP32 arithmetic); a finished tile is announced by one elected
+//               lane per CTA on the LEADER's `ready` barrier (remote mbarrier arrive, default scope);
+//   warps 8-15  ACCUMULATOR warps: TMEM -> registers (tcgen05.ld) every 128 rows, FP64 partials every 32 Ki rows; they arrive
+//               on the leader's `tempty`;
+//   cluster barriers after set-up and before TMEM is freed, and each producer drains its `empty` barriers before
+//   leaving, so no multicast arrive can land in a CTA that has exited.
+// Measured history and what bounded each version: profiles/r02_tf32_pair_stats.txt.
 #include "tf32.cuh"
 
 namespace {
@@ -743,7 +750,7 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   p.ngroups = 0;
   p.nslots = 0;
   p.chunks_per_flush = 256;
-  p.window = 0;
+  p.window = 0;                 // (single-CTA kernel only)
   const size_t gbytes = size_t(grid) * 2 * kMB * kMB * sizeof(double);
   const size_t sbytes = size_t(grid) * kWorkers * 2 * 128 * sizeof(double);
   const int64_t npad = ntiles * kR;
