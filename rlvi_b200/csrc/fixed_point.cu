@@ -53,7 +53,9 @@ struct FpParams {
   int cache_slots;        // FP64 VEC kernels: chunks per thread kept in shared memory
   int l2_head;            // ring mode: keep the head of the vector L2-resident across passes (cache-hinted bulk copies)
   double pi0;             // initial posterior; 0 = the variant's constant (0.95 / 0.5)
+  unsigned long long* trace;   // bring-up only (RLVI_FP_TRACE=1): [round][grid][4] globaltimer stamps, else NULL
 };
+constexpr int kFpTraceRounds = 64;
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
@@ -130,6 +132,8 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = kFpThreads / 32;
   const bool sys = p.world > 1;
+  if (p.trace && round < kFpTraceRounds && threadIdx.x == 0)
+    p.trace[(size_t(round) * gridDim.x + blockIdx.x) * 4 + 0] = gtime_ns();
   const unsigned int buf = round & 1u;
   const unsigned int tag = (unsigned int)((p.call_index << 12) + round + 1ull);     // never 0: round + 1 in [1, 4096)
   unsigned long long* part = reinterpret_cast<unsigned long long*>(p.partials) + size_t(buf) * gridDim.x * 6;
@@ -161,29 +165,43 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     st_ll(mine + 0, a, tag, false);
     st_ll(mine + 2, b, tag, false);
     st_ll(mine + 4, c, tag, false);
+    if (p.trace && round < kFpTraceRounds) p.trace[(size_t(round) * gridDim.x + blockIdx.x) * 4 + 1] = gtime_ns();
   }
   if (blockIdx.x == 0) {
-    // ---- block 0 gathers the block partials (thread t: blocks t, t + 256, ...) and sums them in a fixed order
+    // ---- block 0 gathers the block partials (thread t: blocks t, t + 256, ...) and sums them in a fixed order; the
+    // timeout clock is read on the slow path only (a %globaltimer read per partial sat on every pass's critical path)
     double a = 0.0, b = 0.0;
     double c = (OP2 == OP_SUM) ? 0.0 : (OP2 == OP_MIN ? INFINITY : -INFINITY);
     int failed = 0;
-    for (unsigned int j = threadIdx.x; j < gridDim.x && !failed; j += kFpThreads) {
+    for (unsigned int j = threadIdx.x; j < gridDim.x && !failed; j += 2 * kFpThreads) {
+      // two partials per thread and sweep (blocks j and j + 256), polled TOGETHER: the blocks beyond the first 256 tend
+      // to arrive last, and polling them only after the thread's first partial put a second L2 round trip on the path
+      const bool two = j + kFpThreads < gridDim.x;
       const unsigned long long* src = part + size_t(j) * 6;
-      double x0, x1, x2;
-      const unsigned long long t0 = gtime_ns();
+      const unsigned long long* src2 = two ? part + size_t(j + kFpThreads) * 6 : src;
+      double x0, x1, x2, y0, y1, y2;
+      unsigned long long t0 = 0ull;
       unsigned int spins = 0;
       for (;;) {
         const bool k0 = ld_ll(src + 0, tag, false, x0), k1 = ld_ll(src + 2, tag, false, x1), k2 = ld_ll(src + 4, tag, false, x2);
-        if (k0 && k1 && k2) break;
+        const bool m0 = ld_ll(src2 + 0, tag, false, y0), m1 = ld_ll(src2 + 2, tag, false, y1), m2 = ld_ll(src2 + 4, tag, false, y2);
+        if (k0 && k1 && k2 && m0 && m1 && m2) break;
         if ((++spins & 63u) == 0u) {
           if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
-          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+          const unsigned long long now = gtime_ns();
+          if (t0 == 0ull) t0 = now;
+          if (now - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
         }
       }
       if (!failed) {
         a += x0;
         b += x1;
         c = (OP2 == OP_SUM) ? c + x2 : (OP2 == OP_MIN ? fmin(c, x2) : fmax(c, x2));
+        if (two) {
+          a += y0;
+          b += y1;
+          c = (OP2 == OP_SUM) ? c + y2 : (OP2 == OP_MIN ? fmin(c, y2) : fmax(c, y2));
+        }
       }
     }
     a = warp_sum(a);
@@ -214,6 +232,7 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
         st_ll(dst + 2, tb, tag, sys);
         st_ll(dst + 4, tc, tag, sys);
       }
+      if (p.trace && round < kFpTraceRounds && lane == 0) p.trace[(size_t(round) * gridDim.x) * 4 + 2] = gtime_ns();
     }
   }
   if (warp == 0) {
@@ -222,14 +241,16 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     int failed = 0;
     if (lane < p.world) {
       const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.inbox) + slot + size_t(lane) * 6;
-      const unsigned long long t0 = gtime_ns();
+      unsigned long long t0 = 0ull;        // the timeout clock is read on the slow path only
       unsigned int spins = 0;
       for (;;) {
         const bool k0 = ld_ll(src + 0, tag, sys, ra), k1 = ld_ll(src + 2, tag, sys, rb), k2 = ld_ll(src + 4, tag, sys, rc);
         if (k0 && k1 && k2) break;
         if ((++spins & 63u) == 0u) {
           if (ld_acquire_u32(p.control + 1) != 0u) { failed = 1; break; }
-          if (gtime_ns() - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
+          const unsigned long long now = gtime_ns();
+          if (t0 == 0ull) t0 = now;
+          if (now - t0 > kSpinTimeoutNs) { atomicExch(p.control + 1, 1u); failed = 1; break; }
         }
       }
     }
@@ -251,6 +272,8 @@ __device__ bool grid_allreduce3(const FpParams<T>& p, FpShared& sh, double& v0, 
     }
   }
   __syncthreads();
+  if (p.trace && round < kFpTraceRounds && threadIdx.x == 0)
+    p.trace[(size_t(round) * gridDim.x + blockIdx.x) * 4 + 3] = gtime_ns();
   v0 = sh.total[0];
   v1 = sh.total[1];
   v2 = sh.total[2];
@@ -754,7 +777,6 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   }
   const int64_t chunk0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t cstride = int64_t(gridDim.x) * blockDim.x;
-
   // rho for pass 1 from the constant initial posterior, in the reference's operation order
   double rho_new, rho_old = 0.0, eps;
   if (VARIANT == RLVI_FP_STANDARD) {
@@ -1240,10 +1262,58 @@ int launch_fp(rlvi_ctx* ctx, K kernel, FpParams<T>& p, int64_t n_chunks, cudaStr
   // partials.  All zeroed: LL tags start at 1, so a zeroed (or any earlier call's) word never matches.
   RLVI_CUDA(cudaMemsetAsync(p.control, 0, ctrl + part_bytes, stream));
   if (p.world == 1) p.inbox = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
+  p.trace = nullptr;
+  static const char* trace_env = getenv("RLVI_FP_TRACE");
+  const size_t trace_bytes = size_t(kFpTraceRounds) * grid * 4 * sizeof(unsigned long long);
+  if (trace_env && atoi(trace_env) != 0) {
+    RLVI_CUDA(cudaMalloc(&p.trace, trace_bytes));
+    RLVI_CUDA(cudaMemsetAsync(p.trace, 0, trace_bytes, stream));
+  }
   void* args[] = {&p};
   RLVI_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kFpThreads), args,
                                         dyn_smem, stream));
   RLVI_LAUNCH_CHECK(ctx);
+  if (p.trace) {   // bring-up only: per round, when the blocks finished their trips / stored partials / saw the totals
+    RLVI_CUDA(cudaStreamSynchronize(stream));
+    unsigned long long* h = static_cast<unsigned long long*>(malloc(trace_bytes));
+    cudaMemcpy(h, p.trace, trace_bytes, cudaMemcpyDeviceToHost);
+    unsigned long long prev_done = 0ull;
+    for (int r = 0; r < kFpTraceRounds; ++r) {
+      const unsigned long long* t = h + size_t(r) * grid * 4;
+      if (t[0] == 0ull) break;
+      unsigned long long base = t[0];
+      for (int b = 0; b < grid; ++b) if (t[b * 4] < base) base = t[b * 4];
+      double a_min = 1e30, a_max = 0, a_mean = 0, st_max = 0, done_min = 1e30, done_max = 0, done_mean = 0;
+      int argmax = 0;
+      for (int b = 0; b < grid; ++b) {
+        const double a = double(t[b * 4 + 0] - base), s1 = double(t[b * 4 + 1] - base), dn = double(t[b * 4 + 3] - base);
+        if (a > a_max) { a_max = a; argmax = b; }
+        a_min = a < a_min ? a : a_min;
+        a_mean += a / grid;
+        st_max = s1 > st_max ? s1 : st_max;
+        done_min = dn < done_min ? dn : done_min;
+        done_max = dn > done_max ? dn : done_max;
+        done_mean += dn / grid;
+      }
+      fprintf(stderr, "[fp trace] round %2d: since prev done %7.0f ns | arrive min 0 mean %5.0f max %5.0f (block %d) | partials "
+              "stored by %5.0f | block 0 arrived %5.0f published %5.0f | totals seen min %5.0f mean %5.0f max %5.0f\n", r,
+              prev_done > 0ull ? double((long long)(base - prev_done)) : 0.0, a_mean, a_max, argmax, st_max, double(t[0] - base),
+              double(t[2] - base), done_min, done_mean, done_max);
+      if (grid >= 8) {      // arrival by eighths of the grid (which blocks are late?)
+        fprintf(stderr, "           mean arrival by eighth of the grid:");
+        for (int q = 0; q < 8; ++q) {
+          double m = 0;
+          const int lo = grid * q / 8, hi = grid * (q + 1) / 8;
+          for (int b = lo; b < hi; ++b) m += double(t[b * 4 + 0] - base) / (hi - lo);
+          fprintf(stderr, " %5.0f", m);
+        }
+        fprintf(stderr, "\n");
+      }
+      prev_done = base + (unsigned long long)done_mean;
+    }
+    free(h);
+    cudaFree(p.trace);
+  }
   return RLVI_OK;
 }
 

@@ -137,6 +137,34 @@ __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// BF16 correction products of the mixed mode (NSPLIT == 2): kind::f16, K = 16 per instruction
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = F32, A = B = BF16 (format 1 at bits 7 and 10), both MN-major, N >> 3 at bit 17, M = 256
+__device__ __forceinline__ uint32_t umma_idesc_pair_bf16(int n_cols) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n_cols >> 3) << 17) |
+         (uint32_t(256 >> 4) << 24);
+}
+// 16-bit MN-major operand block (128 features x 16 rows = 4 KiB), SWIZZLE_128B: atom = 64 features (128 B) x 8 rows,
+// LBO = 2048 B between the two feature atoms, SBO = 1024 B between the two 8-row groups (tools/bf16_debug.cu,
+// profiles/r02_bf16_descriptor_probe.txt)
+constexpr int kBlk16Bytes = 4096;
+__device__ __forceinline__ uint64_t umma_desc_bf16(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(2048 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {      // lo -> bits 0..15
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // instruction descriptor of the pair instruction: as umma_idesc, M = 256
 __device__ __forceinline__ uint32_t umma_idesc_pair(int n_cols) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n_cols >> 3) << 17) |
@@ -183,6 +211,21 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
   // FP32 column sums of the last kFlushTiles tiles -> FP64 (lane l keeps columns l, l + 32, l + 64, l + 96)
   auto flush_sums = [&]() {
     if (HAS_SUMS) {
+      if (NSPLIT == 2 && (r4 & 1)) {      // odd rows accumulated chunk c ^ 1 in slot c (see the chunk order below)
+#pragma unroll
+        for (int c = 0; c < (HAS_SUMS ? 4 : 1); c += 2)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const float2 t1 = s1acc[c][k];
+            s1acc[c][k] = s1acc[HAS_SUMS ? c + 1 : 0][k];
+            s1acc[HAS_SUMS ? c + 1 : 0][k] = t1;
+            if (HAS_Y) {
+              const float2 t2 = syacc[(HAS_SUMS && HAS_Y) ? c : 0][k];
+              syacc[(HAS_SUMS && HAS_Y) ? c : 0][k] = syacc[(HAS_SUMS && HAS_Y) ? c + 1 : 0][k];
+              syacc[(HAS_SUMS && HAS_Y) ? c + 1 : 0][k] = t2;
+            }
+          }
+      }
 #pragma unroll
       for (int c = 0; c < (HAS_SUMS ? 4 : 1); ++c)
 #pragma unroll
@@ -239,16 +282,19 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
         if (i < nfb) {
           const bool sums = HAS_SUMS && (i == 0);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c0 = 0; c0 < 4; ++c0) {
+            // mixed mode: odd rows of a pass take the chunks in the order 1, 0, 3, 2, so that the 8-byte BF16 stores of the
+            // four rows spread over both halves of the 128-byte lines (2 wavefronts per store instead of 4)
+            const int c = (NSPLIT == 2) ? (c0 ^ (r4 & 1)) : c0;
             float4* ptr = reinterpret_cast<float4*>(sb + i * kBlkBytes + c * kChunkBytes + pass * 512 + off0);
             const float4 x = *ptr;
             const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
             if (sums) {
-              s1acc[HAS_SUMS ? c : 0][0] = f2fma(xa, c1v, s1acc[HAS_SUMS ? c : 0][0]);
-              s1acc[HAS_SUMS ? c : 0][1] = f2fma(xb, c1v, s1acc[HAS_SUMS ? c : 0][1]);
+              s1acc[HAS_SUMS ? c0 : 0][0] = f2fma(xa, c1v, s1acc[HAS_SUMS ? c0 : 0][0]);
+              s1acc[HAS_SUMS ? c0 : 0][1] = f2fma(xb, c1v, s1acc[HAS_SUMS ? c0 : 0][1]);
               if (HAS_Y) {
-                syacc[(HAS_SUMS && HAS_Y) ? c : 0][0] = f2fma(xa, cyv, syacc[(HAS_SUMS && HAS_Y) ? c : 0][0]);
-                syacc[(HAS_SUMS && HAS_Y) ? c : 0][1] = f2fma(xb, cyv, syacc[(HAS_SUMS && HAS_Y) ? c : 0][1]);
+                syacc[(HAS_SUMS && HAS_Y) ? c0 : 0][0] = f2fma(xa, cyv, syacc[(HAS_SUMS && HAS_Y) ? c0 : 0][0]);
+                syacc[(HAS_SUMS && HAS_Y) ? c0 : 0][1] = f2fma(xb, cyv, syacc[(HAS_SUMS && HAS_Y) ? c0 : 0][1]);
               }
             }
             const float2 za = f2mul(xa, scv), zb = f2mul(xb, scv);
@@ -257,6 +303,18 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
             if (NSPLIT == 3) {
               const float2 la = f2fma(ha, m1v, za), lb = f2fma(hb, m1v, zb);       // exact remainders
               *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ptr) + lo_off) = make_float4(la.x, la.y, lb.x, lb.y);
+            }
+            if (NSPLIT == 2) {
+              // mixed mode: the two correction products run as BF16 (K = 16 per instruction, half the tensor time and half
+              // the operand bytes of a TF32 pass): z to 8 bits and the exact remainder to 8 bits, in the 16-bit operands'
+              // own MN-major layout.  Features 32 c + 4 q .. + 3 of row rr: 8 bytes in 16-byte unit 4 (c & 1) + (q >> 1)
+              // (XOR rr & 7) of the row's 128-byte line, feature atom c >> 1, row group rr >> 3.
+              const float2 la = f2fma(ha, m1v, za), lb = f2fma(hb, m1v, zb);
+              const uint32_t o16 = uint32_t((c >> 1) * 2048 + (rr >> 3) * 1024 + (rr & 7) * 128 +
+                                            (((4 * (c & 1) + (q >> 1)) ^ (rr & 7)) << 4) + (q & 1) * 8);
+              unsigned char* h16 = sb + nfb * kBlkBytes + i * kBlk16Bytes + o16;
+              *reinterpret_cast<uint2*>(h16) = make_uint2(pack_bf16x2(za.x, za.y), pack_bf16x2(zb.x, zb.y));
+              *reinterpret_cast<uint2*>(h16 + nfb * kBlk16Bytes) = make_uint2(pack_bf16x2(la.x, la.y), pack_bf16x2(lb.x, lb.y));
             }
           }
         }
@@ -377,7 +435,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int fb_a = 2 * pa + int(rank), fb_b = 2 * pb + int(rank);
   const int nfb = diag ? 1 : 2;
   const uint32_t a_off = 0u, b_off = diag ? 0u : uint32_t(kBlkBytes);
-  const int stage_bytes = nfb * kBlkBytes * (NSPLIT == 3 ? 2 : 1);
+  const int stage_bytes = nfb * kBlkBytes * (NSPLIT == 1 ? 1 : 2);      // mixed mode: 8 KiB TF32 hi + 2 x 4 KiB BF16 per block
   int nst = (kSmemBudget - kPairStages * kCoefBytes) / stage_bytes;
   if (nst > kPairStages) nst = kPairStages;
   const uint32_t coef_off = uint32_t(nst) * uint32_t(stage_bytes);      // coefficient slots behind the stages
@@ -488,6 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
       const uint32_t idesc = umma_idesc_pair(256);
+      const uint32_t idesc16 = umma_idesc_pair_bf16(256);
       const uint32_t lo_off = uint32_t(nfb * kBlkBytes);   // Z_lo blocks follow the Z_hi blocks of a stage
       const uint64_t dconst = umma_desc(0);
       auto desc = [&](uint32_t addr) { return dconst | uint64_t((addr & 0x3FFFFu) >> 4); };
@@ -524,6 +583,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             tc2_mma_tf32(dcol, desc(kb + lo_off + a_off), b_hi, idesc, 1u);
             tc2_mma_tf32(dcol, a_hi, desc(kb + lo_off + b_off), idesc, 1u);
           }
+        }
+        if (NSPLIT == 2) {      // lo . hi + hi . lo in BF16: one K = 16 instruction each for the whole tile
+          const uint32_t h16 = sb + uint32_t(nfb * kBlkBytes), l16 = h16 + uint32_t(nfb * kBlk16Bytes);
+          const uint32_t a16 = a_off / 2u, b16 = b_off / 2u;     // block index x 4 KiB
+          tc2_mma_bf16(dcol, umma_desc_bf16(l16 + a16), umma_desc_bf16(h16 + b16), idesc16, 1u);
+          tc2_mma_bf16(dcol, umma_desc_bf16(h16 + a16), umma_desc_bf16(l16 + b16), idesc16, 1u);
         }
         tc2_commit_both(&empty_bar[s]);                                        // stage free in both CTAs
         if (tin == kTpc - 1 || it == my_tiles - 1) tc2_commit_both(&tfull_bar[buf]);   // chunk complete in both TMEMs
@@ -681,13 +746,18 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   pp.nbp = (nb + 1) / 2;                                // d = 257..384: the fourth block is zero-filled by the TMA
   pp.ntypes = (pp.nbp == 1) ? 1 : 3;
 
-  const int variant = (precision == RLVI_TF32X1 ? 0 : 2) + (p.y ? 1 : 0);
-  const void* fns[4] = {(const void*)gram_tf32_pair_kernel<1, false>, (const void*)gram_tf32_pair_kernel<1, true>,
-                        (const void*)gram_tf32_pair_kernel<3, false>, (const void*)gram_tf32_pair_kernel<3, true>};
+  // RLVI_TF32X3 = the ~1e-6 mode: TF32 hi.hi + the two correction products.  By default the corrections run as BF16
+  // (NSPLIT = 2: a third less tensor time); RLVI_TF32_PURE3=1 keeps all three passes in TF32 (NSPLIT = 3).
+  static const char* pure_env = getenv("RLVI_TF32_PURE3");
+  const int nsplit = (precision == RLVI_TF32X1) ? 1 : ((pure_env && atoi(pure_env) != 0) ? 3 : 2);
+  const int variant = (nsplit == 1 ? 0 : (nsplit == 3 ? 2 : 4)) + (p.y ? 1 : 0);
+  const void* fns[6] = {(const void*)gram_tf32_pair_kernel<1, false>, (const void*)gram_tf32_pair_kernel<1, true>,
+                        (const void*)gram_tf32_pair_kernel<3, false>, (const void*)gram_tf32_pair_kernel<3, true>,
+                        (const void*)gram_tf32_pair_kernel<2, false>, (const void*)gram_tf32_pair_kernel<2, true>};
   const void* fn = fns[variant];
   // once per (device, kernel): the shared-memory opt-in and how many pairs can be resident at once (one CTA per SM,
   // the two SMs of a TPC per pair) -- both are host-side driver calls of ~1 ms
-  static int cached_pairs[64][4];
+  static int cached_pairs[64][6];
   const int dev_slot = (ctx->device >= 0 && ctx->device < 64) ? ctx->device : 0;
   int max_pairs = cached_pairs[dev_slot][variant];
   if (max_pairs == 0) {
@@ -790,12 +860,13 @@ int rlvi_tf32_pair_moments(rlvi_ctx* ctx, const CUtensorMap& tmap, const CUtenso
   }
   pp.b = p;
 
-  if (precision == RLVI_TF32X1) {
-    if (p.y) gram_tf32_pair_kernel<1, true><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp);
-    else gram_tf32_pair_kernel<1, false><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp);
-  } else {
-    if (p.y) gram_tf32_pair_kernel<3, true><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp);
-    else gram_tf32_pair_kernel<3, false><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp);
+  switch (variant) {
+    case 0: gram_tf32_pair_kernel<1, false><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
+    case 1: gram_tf32_pair_kernel<1, true><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
+    case 2: gram_tf32_pair_kernel<3, false><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
+    case 3: gram_tf32_pair_kernel<3, true><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
+    case 4: gram_tf32_pair_kernel<2, false><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
+    default: gram_tf32_pair_kernel<2, true><<<grid, kThreads, kSmemTotal, st>>>(tmap, tmap3, pp); break;
   }
   RLVI_LAUNCH_CHECK(ctx);
   if (p.stats) {     // bring-up only: synchronise and print the per-role cycle counters (mean over the CTAs of a type)

@@ -187,6 +187,12 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
         double a[8];
 #pragma unroll
         for (int I = 0; I < 8; ++I) a[I] = we * b[I];
+        // ptxas sinks each DMUL to just before its first DMMA (one shared temporary), which exposes the DMUL -> DMMA
+        // latency eight times per k-group; a never-taken store that reads all eight products pins them here
+        if (p.n < 0) {
+#pragma unroll
+          for (int I = 0; I < 8; ++I) reinterpret_cast<volatile double*>(smem)[lane + 32 * I] = a[I];
+        }
         int idx = 0;
 #pragma unroll
         for (int I = 0; I < 8; ++I) {
