@@ -75,7 +75,7 @@ def test_sharded_em_step_matches_oracle(n):
         assert p.exitcode == 0
     X, y, theta = synth.logistic_data(n, d, seed=7)
     ref = rlvi_np.em_step_logistic(X, y, np.concatenate([[0.1], theta]))
-    tol = max(1e-9, 8 * 2.0 ** -52 / float(ref["pi"].mean()))
+    tol = max(1e-9, 4 * 2.0 ** -53 / float(ref["pi"].mean()))
     for rep in range(3):
         results = [g[1][rep][0] for g in got]
         assert all(r["iters"] == ref["iters"] for r in results)
