@@ -104,6 +104,30 @@ def test_moments_f32_single_pass_tf32_is_bounded():
     assert rel(m1["G"], r["G"]) < 2e-4            # 2^-11 operand rounding, zero-mean: ~1e-3 / sqrt(rows)
 
 
+@pytest.mark.parametrize("n,d,power,with_y", [(30000, 512, 2, False), (9000, 256, 1, True), (5000, 388, 2, True)])
+def test_moments_f32_correction_modes_agree(n, d, power, with_y, monkeypatch):
+    """The ~1e-6 mode of the CTA-pair kernel runs its two correction products (lo.hi + hi.lo) as BF16 by default and as
+    TF32 with RLVI_TF32_PURE3=1: both meet the oracle at the FP32 tolerance, and they agree with each other far below it
+    (the BF16 rounding of the corrections is a 2^-19 relative, zero-mean perturbation of each product)."""
+    rng = np.random.default_rng(n)
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    X[:, :3] += 2.0
+    w = rng.random(n) ** 3
+    y = rng.normal(size=n) if with_y else None
+    r = oracle_moments(X, w, y, power)
+    monkeypatch.delenv("RLVI_TF32_PURE3", raising=False)
+    mixed = gpu_moments(X, w, y, power)
+    monkeypatch.setenv("RLVI_TF32_PURE3", "1")
+    pure = gpu_moments(X, w, y, power)
+    for m in (mixed, pure):
+        assert rel(m["G"], r["G"]) < TOL32
+        assert rel(m["S1"], r["S1"]) < TOL32
+        if with_y:
+            assert rel(m["Sy"], r["Sy"]) < TOL32
+    assert rel(mixed["G"], pure["G"]) < 3e-6
+    assert np.array_equal(mixed["S1"], pure["S1"])               # column sums do not go through the tensor core
+
+
 def test_moments_f32_deterministic_and_linear():
     rng = np.random.default_rng(11)
     X = rng.normal(size=(70001, 512)).astype(np.float32)
