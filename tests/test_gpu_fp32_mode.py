@@ -125,7 +125,9 @@ def test_moments_f32_correction_modes_agree(n, d, power, with_y, monkeypatch):
         if with_y:
             assert rel(m["Sy"], r["Sy"]) < TOL32
     assert rel(mixed["G"], pure["G"]) < 3e-6
-    assert np.array_equal(mixed["S1"], pure["S1"])               # column sums do not go through the tensor core
+    # column sums do not go through the tensor core; the two modes split the row tiles over the pair types differently,
+    # so their FP32 partial sums group differently
+    assert rel(mixed["S1"], pure["S1"]) < 1e-6
 
 
 def test_moments_f32_deterministic_and_linear():
