@@ -388,6 +388,9 @@ struct ECache {
   int ring;        // != 0: the buffer is a per-WARP TMA prefetch ring instead (HBM-sized vectors)
   uint64_t* bars;  // ring mode: [warps][kFpRingDepth] mbarriers (kernel lifetime; phases persist across passes)
   uint32_t phase;  // ring mode: bit s = parity to wait for on this warp's slot s
+  int armed;       // ring mode: slots 0 .. armed - 1 already hold (or are receiving) the NEXT pass's first trips: e[] does not
+                   // change after pass 1, so a pass ends by issuing the next pass's first copies and their latency runs
+                   // under the grid reduction instead of in front of the first trip
   // ring mode, L2 residency: the vector (512 MiB at the headline shape) is streamed once per pass and plain LRU keeps
   // none of it in the 126 MB L2.  The first `head_trips` trips of every warp's segment (~75 MiB in all) are loaded under
   // an L2 evict_last policy, the rest under evict_first, so that head is served from L2 in every pass after the first
@@ -483,30 +486,43 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
     const int64_t lo = wg * seg < nvec ? wg * seg : nvec;
     const int64_t hi = (lo + seg < nvec) ? lo + seg : nvec;
     const int64_t ntrips = (hi - lo) / kWarpTrip;
+    // the segment's partial last trip goes through the ring too (a shorter copy; lanes beyond it read zeros: e = 0 adds nothing
+    // to either sum) instead of a batch of direct loads whose L2 latency stood at the end of every pass
+    const int rem = int((hi - lo) - ntrips * kWarpTrip);
+    const int64_t nt = ntrips + (rem > 0 ? 1 : 0);
     double2* ringw = ec.buf + size_t(warp) * kFpRingDepth * kWarpTrip;
     uint64_t* bar = ec.bars + warp * kFpRingDepth;
     uint32_t phase = ec.phase;
     auto issue = [&](int64_t j, int slot) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(&bar[slot], kWarpTrip * 16);
+        const uint32_t bytes = (j < ntrips) ? uint32_t(kWarpTrip * 16) : uint32_t(rem) * 16u;
+        mbar_arrive_expect_tx(&bar[slot], bytes);
         if (ec.head_trips > 0)
-          bulk_g2s_hint(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, kWarpTrip * 16, &bar[slot],
+          bulk_g2s_hint(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, bytes, &bar[slot],
                         j < ec.head_trips ? ec.pol_last : ec.pol_first);
         else
-          bulk_g2s(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, kWarpTrip * 16, &bar[slot]);
+          bulk_g2s(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, bytes, &bar[slot]);
       }
     };
+    if (ec.armed == 0) {          // the first ring pass; later passes were armed by their predecessor
 #pragma unroll
-    for (int j = 0; j < kFpRingDepth - 1; ++j)
-      if (j < ntrips) issue(j, j);
+      for (int j = 0; j < kFpRingDepth - 1; ++j)
+        if (j < nt) issue(j, j);
+    }
     int rd = 0, wr = kFpRingDepth - 1;
-    for (int64_t j = 0; j < ntrips; ++j) {
-      if (j + kFpRingDepth - 1 < ntrips) issue(j + kFpRingDepth - 1, wr);   // slot wr was read in iteration j - 1
+    for (int64_t j = 0; j < nt; ++j) {
+      if (j + kFpRingDepth - 1 < nt) issue(j + kFpRingDepth - 1, wr);   // slot wr was read in iteration j - 1
       mbar_wait(&bar[rd], (phase >> rd) & 1u);
       phase ^= 1u << rd;
       double2 v[kFpUnroll];
+      if (j < ntrips) {
 #pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) v[u] = ringw[rd * kWarpTrip + u * 32 + lane];
+        for (int u = 0; u < kFpUnroll; ++u) v[u] = ringw[rd * kWarpTrip + u * 32 + lane];
+      } else {
+#pragma unroll
+        for (int u = 0; u < kFpUnroll; ++u)
+          v[u] = (u * 32 + lane < rem) ? ringw[rd * kWarpTrip + u * 32 + lane] : make_double2(0.0, 0.0);
+      }
       __syncwarp();                              // every lane has its data: the slot may be re-armed next trip
       double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
       if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
@@ -519,40 +535,9 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
       } else {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
 #pragma unroll 1
         for (int u = 0; u < kFpUnroll; ++u) {
-          const double2 w = ld_e2(ev + lo + j * kWarpTrip + u * 32 + lane);
-          double pn, d;
-          post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
-          s1a += pn;
-          s2a = fma(d, d, s2a);
-          post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
-          s1b += pn;
-          s2b = fma(d, d, s2b);
-        }
-      }
-      rd = (rd + 1 == kFpRingDepth) ? 0 : rd + 1;
-      wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
-    }
-    ec.phase = phase;
-    // remainder of the warp's segment (< one trip): one predicated batch of direct loads, zero-filled (e = 0 adds
-    // nothing to either sum), through the same fast trip -- the IEEE divisions cost ~5x as much per sample
-    {
-      const int64_t r0 = lo + ntrips * kWarpTrip + lane;
-      double2 v[kFpUnroll];
-#pragma unroll
-      for (int u = 0; u < kFpUnroll; ++u) v[u] = (r0 + u * 32 < hi) ? ld_e2(ev + r0 + u * 32) : make_double2(0.0, 0.0);
-      double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
-      if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
-      else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
-      if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
-        s1a += t1a;
-        s1b += t1b;
-        q2sa += q2a;
-        q2sb += q2b;
-      } else {
-#pragma unroll 1
-        for (int u = 0; u < kFpUnroll; ++u) {
-          if (r0 + u * 32 < hi) {
-            const double2 w = ld_e2(ev + r0 + u * 32);
+          const int64_t i = lo + j * kWarpTrip + u * 32 + lane;
+          if (i < hi) {
+            const double2 w = ld_e2(ev + i);
             double pn, d;
             post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
             s1a += pn;
@@ -563,7 +548,18 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
           }
         }
       }
+      rd = (rd + 1 == kFpRingDepth) ? 0 : rd + 1;
+      wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
     }
+    // every slot has been read (the __syncwarp of the last trip): arm the next pass's first trips now
+    ec.armed = 0;
+#pragma unroll
+    for (int j = 0; j < kFpRingDepth - 1; ++j)
+      if (j < nt) {
+        issue(j, j);
+        ec.armed = j + 1;
+      }
+    ec.phase = phase;
     c = nvec;                                    // the grid-stride loops below have nothing left to do
   }
   for (; c + (kFpUnroll - 1) * stride < nvec; c += kFpUnroll * stride, slot0 += kFpUnroll) {
@@ -760,6 +756,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
   __shared__ uint64_t fp_ring_bars[(kFpThreads / 32) * kFpRingDepth];
   ec.bars = fp_ring_bars;
   ec.phase = 0u;
+  ec.armed = 0;
   ec.head_trips = 0;
   ec.pol_last = ec.pol_first = 0ull;
   if (ec.ring && p.l2_head) {
@@ -897,6 +894,12 @@ __global__ void __launch_bounds__(kFpThreads) fp_kernel_f64(const FpParams<doubl
     }
   }
 
+  // ring mode: the last stream pass armed copies for a pass that will not run -- let them land before the CTA can exit
+  if (ec.ring) {
+    uint64_t* bar = ec.bars + (threadIdx.x >> 5) * kFpRingDepth;
+    for (int sl = 0; sl < ec.armed; ++sl) mbar_wait(&bar[sl], (ec.phase >> sl) & 1u);
+    ec.armed = 0;
+  }
   // final pass: write the last pi' with the reference's own expression (single correctly rounded
   // division), then the variant's normalisation
   double norm = 1.0;
@@ -1361,9 +1364,10 @@ static int fp_cache_slots(int64_t n) {
     const int v = atoi(env);
     return v < 0 ? -1 : (v > kFpCacheSlots ? kFpCacheSlots : v);
   }
-  // <= 2^25 samples (16 trips per thread on a full grid): keep the head of the vector resident
-  // (measured 0.58 -> 0.50 ms at 2^23); larger: the buffer becomes a cp.async prefetch ring (-1)
-  return n <= (int64_t(1) << 25) ? kFpCacheSlots : -1;
+  // <= 2^22 samples: keep the head of the vector resident in shared memory; larger: the buffer becomes a bulk-copy prefetch
+  // ring (-1) -- from 2^23 samples on the ring wins even while the vector is L2 resident (12.9 vs 14.4 us per pass at 2^23,
+  // 24.1 vs 27.9 at 2^24, 9.0 vs 8.1 at 2^22: tools/fp_pass_time.py), because its copies run ahead of the arithmetic
+  return n <= (int64_t(1) << 22) ? kFpCacheSlots : -1;
 }
 
 extern "C" int rlvi_fixed_point_f64(rlvi_ctx* ctx, int variant, const double* losses, const double* scale,
