@@ -2,7 +2,7 @@
 # Final single-GPU evidence pass (round 2): full GPU suite, bench lines (no profiler), then the ncu launch list + DRAM traffic
 # at full size and one --set full capture of the three step kernels at N = 2^23 (ncu replays each kernel ~40 times).
 cd "$GRAFT_REPO_ROOT"
-R=r02g
+R=r02h
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > gpurun_out/${R}_pytest.log; cat gpurun_out/${R}_pytest.log
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/${R}_clocks.csv & SMI_PID=$!
 timeout 400 python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err; echo "bench rc=$?"
