@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram64_kernel(const GramParam
         double a[8];
 #pragma unroll
         for (int I = 0; I < 8; ++I) a[I] = we * b[I];
-        // ptxas sinks each DMUL to just before its first DMMA (one shared temporary), which exposes the DMUL -> DMMA
-        // latency eight times per k-group; a never-taken store that reads all eight products pins them here
+        // ptxas sinks each DMUL to just before its first DMMA (one shared temporary); a never-taken store that reads all
+        // eight products pins them here (same-box A/B at N = 2^26: 9.620 -> 9.598 ms -- the scheduler's other warp
+        // already covered most of that latency)
         if (p.n < 0) {
 #pragma unroll
           for (int I = 0; I < 8; ++I) reinterpret_cast<volatile double*>(smem)[lane + 32 * I] = a[I];
