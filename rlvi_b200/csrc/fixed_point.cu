@@ -1356,11 +1356,11 @@ static int fixed_point_f64_impl(rlvi_ctx* ctx, int variant, const double* losses
                                 double* e_work, int64_t n, double tol, int maxiter, double pi0, double* pi_out,
                                 rlvi_fp_result* result, const rlvi_fp_dist* dist, void* stream);
 
-// Shared-memory residency of e[]: covers ~40 % of an 8-GPU shard of the headline shape, ~5 % of the full
-// vector.  RLVI_FP_CACHE_SLOTS overrides (experiments).
+// How the later passes get e[]: resident head in shared memory (small shards) or the bulk-copy ring.
+// RLVI_FP_CACHE_SLOTS overrides (experiments, tests).
 static int fp_cache_slots(int64_t n) {
-  static const char* env = getenv("RLVI_FP_CACHE_SLOTS");
-  if (env) {
+  const char* env = getenv("RLVI_FP_CACHE_SLOTS");       // read per call: tests switch it
+  if (env && *env) {
     const int v = atoi(env);
     return v < 0 ? -1 : (v > kFpCacheSlots ? kFpCacheSlots : v);
   }

@@ -151,6 +151,30 @@ def test_fixed_point_ragged_and_unaligned(dev, n):
     assert relmax(pi2.cpu().numpy(), ref) < pi_tol(ref)
 
 
+@pytest.mark.parametrize("n", [2, 513, 4098, 70001, 606209, 2500003])
+@pytest.mark.parametrize("slots", ["-1", "0", "8"])
+def test_fixed_point_streaming_modes_on_ragged_sizes(dev, n, slots, monkeypatch):
+    """The bulk-copy ring (RLVI_FP_CACHE_SLOTS=-1; the default above 2^22 samples per GPU), no residency (0) and a partial
+    resident head (8), forced onto sizes where warps own no trip at all, only a partial trip, or whole trips plus a ragged
+    rest -- the partial last trip of a warp's segment goes through the ring as a shorter copy, and every pass arms the next
+    pass's first copies, which the kernel must drain when the loop ends early."""
+    from rlvi_b200 import ops
+    monkeypatch.setenv("RLVI_FP_CACHE_SLOTS", slots)
+    rng = np.random.default_rng(n)
+    losses = 0.5 * rng.chisquare(1, size=n)
+    ref, eps, k, err = rlvi_np.fixed_point_trace(losses)
+    pi, res = ops.fixed_point(cu(losses, dev))
+    r = ops.read_result(res)
+    assert r["iters"] == k
+    assert relmax(pi.cpu().numpy(), ref) < pi_tol(ref)
+    # a stop after very few passes (tol large, then maxiter = 2): armed copies of a pass that never runs
+    for kw in ({"tol": 0.5}, {"maxiter": 2}):
+        ref2, _, k2, _ = rlvi_np.fixed_point_trace(losses, **kw)
+        pi2, res2 = ops.fixed_point(cu(losses, dev), **kw)
+        assert ops.read_result(res2)["iters"] == k2
+        assert relmax(pi2.cpu().numpy(), ref2) < pi_tol(ref2)
+
+
 def test_fixed_point_scale_and_precomputed_e(dev):
     from rlvi_b200 import ops
     rng = np.random.default_rng(5)
