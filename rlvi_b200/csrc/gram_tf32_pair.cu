@@ -44,6 +44,11 @@ using namespace tf32;
 constexpr int kPairStages = 12;             // upper bound; the ring uses min(kPairStages, budget / stage bytes)
 constexpr int kPairTypes = 3;
 constexpr int kWorkers = 6;                 // transform warps per CTA: warps 2-7
+#ifndef RLVI_PAIR_WARPS_PER_TILE
+#define RLVI_PAIR_WARPS_PER_TILE 1
+#endif
+constexpr int kWarpsPerTile = RLVI_PAIR_WARPS_PER_TILE;   // 1: a warp transforms a whole 16-row tile; 2: two warps share it (8 rows each)
+constexpr int kTeams = kWorkers / kWarpsPerTile;
 constexpr int kCoefBytes = 256;             // per stage: s, c1, cy of the tile's 16 rows (64 B each)
 constexpr int kCoefThreads = 256;
 
@@ -257,9 +262,11 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
 
   int done = 0;
   long long t_full = 0, t_busy = 0;
-  int s = worker % nst;
-  uint32_t ph = uint32_t(worker / nst) & 1u;
-  for (int it = worker; it < my_tiles; it += kWorkers) {
+  const int team = worker / kWarpsPerTile, half = worker % kWarpsPerTile;
+  constexpr int kPassesPerWarp = (kR / 4) / kWarpsPerTile;
+  int s = team % nst;
+  uint32_t ph = uint32_t(team / nst) & 1u;
+  for (int it = team; it < my_tiles; it += kTeams) {
     const long long k1 = p.stats ? clock64() : 0;
     // see gram_tf32.cu: `empty` one phase back first, so that `full` cannot be mistaken for the previous phase
     ok = wait_or_abort(&empty_bar[s], ph ^ 1u, p.err) && wait_or_abort(&full_bar[s], ph, p.err);
@@ -271,7 +278,8 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
     // FP64 instructions issued while the tensor pipe is busy wait for it (stall_math was 47 % of these warps' time)
     const float* cf = reinterpret_cast<const float*>(smem + cx.coef_off + uint32_t(s) * kCoefBytes);
 #pragma unroll
-    for (int pass = 0; pass < kR / 4; ++pass) {
+    for (int pp = 0; pp < kPassesPerWarp; ++pp) {
+      const int pass = half * kPassesPerWarp + pp;
       const int rr = pass * 4 + r4;
       const float sc = cf[rr];
       const float c1 = cx.c1_is_sc ? sc : cf[kR + rr];
@@ -324,7 +332,7 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(cx.ready_remote + uint32_t(s) * 8u);   // the leader's barrier: 1 + 1 warps per tile
     if ((++done % kFlushTiles) == 0) flush_sums();
-    s += kWorkers;
+    s += kTeams;
     while (s >= nst) {
       s -= nst;
       ph ^= 1u;
@@ -332,8 +340,8 @@ __device__ __forceinline__ void pair_transform_warp(const Tf32Params& p, const P
     if (p.stats) t_busy += clock64() - k2;
   }
   if (p.stats && lane == 0 && worker == 0) {
-    p.stats[size_t(blockIdx.x) * 8 + 1] = t_full * kWorkers;      // scaled to "per tile of the CTA" like the other roles
-    p.stats[size_t(blockIdx.x) * 8 + 2] = t_busy * kWorkers;
+    p.stats[size_t(blockIdx.x) * 8 + 1] = t_full * kTeams;      // scaled to "per tile of the CTA" like the other roles
+    p.stats[size_t(blockIdx.x) * 8 + 2] = t_busy * kTeams;
   }
   if (ok) {
     flush_sums();
@@ -446,7 +454,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&ready_bar[s], 2);      // the tile's transform warp of each CTA
+      mbar_init(&ready_bar[s], 2 * kWarpsPerTile);      // the tile's transform warp(s) of each CTA
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -495,12 +503,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const long long t_begin = clock64();
       bool ok = true;
       for (int it = 0; it < my_tiles; ++it) {
-        const long long c0 = clock64();
+        const long long c0 = p.stats ? clock64() : 0;
         if (!wait_or_abort(&empty_bar[s], ph ^ 1u, p.err)) {
           ok = false;
           break;
         }
-        t_wait += clock64() - c0;
+        if (p.stats) t_wait += clock64() - c0;
         const int row0 = (slot + it * nslots) * kR;
         const uint32_t sb = smem_base + uint32_t(s) * uint32_t(stage_bytes);
         const bool c1_sep = (pp.coef_c1 != pp.coef_sc);
@@ -558,17 +566,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int ch = it / kTpc;
         const int tin = it - ch * kTpc;
         const int buf = ch & 1;
-        const long long c0 = clock64();
+        const long long c0 = p.stats ? clock64() : 0;      // (the issuer's loop is on the critical path: no clock reads unless asked)
         if (tin == 0) {
           ok = wait_or_abort_cluster(&tempty_bar[buf], (uint32_t(ch >> 1) & 1u) ^ 1u, p.err);
           if (!ok) break;
           tc_fence_after();
         }
-        const long long c1 = clock64();
+        const long long c1 = p.stats ? clock64() : 0;
         ok = wait_or_abort_cluster(&ready_bar[s], ph, p.err);
         if (!ok) break;
         tc_fence_after();
-        const long long c2 = clock64();
+        const long long c2 = p.stats ? clock64() : 0;
         t_tempty += c1 - c0;
         t_ready += c2 - c1;
         const uint32_t sb = smem_base + uint32_t(s) * uint32_t(stage_bytes);
@@ -592,7 +600,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         tc2_commit_both(&empty_bar[s]);                                        // stage free in both CTAs
         if (tin == kTpc - 1 || it == my_tiles - 1) tc2_commit_both(&tfull_bar[buf]);   // chunk complete in both TMEMs
-        t_issue += clock64() - c2;
+        if (p.stats) t_issue += clock64() - c2;
         if (++s == nst) {
           s = 0;
           ph ^= 1u;
