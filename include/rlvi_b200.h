@@ -206,9 +206,11 @@ int rlvi_weighted_moments_centered_f64(rlvi_ctx* ctx, const double* X, const dou
 /* ---- FP32-stored samples (SURVEY.md section 8d "FP32 mode"; BASELINE.json config 3: N = 2^24, d = 512) ---------
  * X is float32 [n][d] row-major; every per-sample vector (y, weights, losses, e) and every statistic stays FP64.
  * The Gram contraction runs on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
- *   RLVI_TF32X3  three TF32 products per term (hi*hi + lo*hi + hi*lo) with short FP32 accumulation chains flushed
- *                into FP64: the statistics agree with an FP64 evaluation on the same float32 samples to ~1e-6
- *                (the 1e-5 FP32 tolerance of BASELINE.json's north_star); default;
+ *   RLVI_TF32X3  three products per term (hi*hi + lo*hi + hi*lo; z = hi + lo with hi the TF32 rounding) with short FP32
+ *                accumulation chains flushed into FP64: the statistics agree with an FP64 evaluation on the same float32
+ *                samples to ~1e-6 (the 1e-5 FP32 tolerance of BASELINE.json's north_star); default.  On the CTA-pair
+ *                kernel (d > 128) the two correction products run as BF16 (kind::f16), which keeps that accuracy at two
+ *                thirds of the tensor time; RLVI_TF32_PURE3=1 in the environment keeps all three in TF32;
  *   RLVI_TF32X1  one TF32 product per term (operands rounded to 11 bits, zero-mean error): 3x fewer tensor-core
  *                flops, ~1e-3 / sqrt(rows) relative accuracy.
  * Same output layout as rlvi_weighted_moments_f64.  Replaces utils.py:82-84 (power = 2), rlvi.py:70-71,79-80 and
