@@ -493,16 +493,46 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
     double2* ringw = ec.buf + size_t(warp) * kFpRingDepth * kWarpTrip;
     uint64_t* bar = ec.bars + warp * kFpRingDepth;
     uint32_t phase = ec.phase;
+    // The trips are bound by issue slots (~200 SASS instructions per 16-sample trip and warp, profiles/r02_fixed_point_trace.txt),
+    // so the loop works on 32-bit shared-memory addresses formed ONCE per pass (the generic-pointer helpers re-derive the
+    // shared window on every call) and tests the sums for non-finite values once per PASS and lane instead of per trip.
+    const uint32_t ring_s = smem_u32(ringw), bar_s = smem_u32(bar);
+    const uint32_t lane_s = ring_s + uint32_t(lane) * 16u;
+    const double2* gsrc = ev + lo;
     auto issue = [&](int64_t j, int slot) {
       if (lane == 0) {
         const uint32_t bytes = (j < ntrips) ? uint32_t(kWarpTrip * 16) : uint32_t(rem) * 16u;
-        mbar_arrive_expect_tx(&bar[slot], bytes);
+        const uint32_t b32 = bar_s + uint32_t(slot) * 8u, dst = ring_s + uint32_t(slot) * uint32_t(kWarpTrip * 16);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
         if (ec.head_trips > 0)
-          bulk_g2s_hint(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, bytes, &bar[slot],
-                        j < ec.head_trips ? ec.pol_last : ec.pol_first);
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+              "l"(gsrc + j * kWarpTrip), "r"(bytes), "r"(b32), "l"(j < ec.head_trips ? ec.pol_last : ec.pol_first)
+              : "memory");
         else
-          bulk_g2s(ringw + slot * kWarpTrip, ev + lo + j * kWarpTrip, bytes, &bar[slot]);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                       "l"(gsrc + j * kWarpTrip), "r"(bytes), "r"(b32)
+                       : "memory");
       }
+    };
+    auto wait_slot = [&](int slot) {
+      const uint32_t b32 = bar_s + uint32_t(slot) * 8u, parity = (phase >> slot) & 1u;
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(b32), "r"(parity)
+            : "memory");
+      } while (!ok);
+      phase ^= 1u << slot;
+    };
+    auto lds2 = [](uint32_t addr) {
+      double2 r;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr) : "memory");
+      return r;
     };
     if (ec.armed == 0) {          // the first ring pass; later passes were armed by their predecessor
 #pragma unroll
@@ -512,44 +542,37 @@ __device__ __forceinline__ void stream_pass_vec(const double* e, ECache& ec, int
     int rd = 0, wr = kFpRingDepth - 1;
     for (int64_t j = 0; j < nt; ++j) {
       if (j + kFpRingDepth - 1 < nt) issue(j + kFpRingDepth - 1, wr);   // slot wr was read in iteration j - 1
-      mbar_wait(&bar[rd], (phase >> rd) & 1u);
-      phase ^= 1u << rd;
+      wait_slot(rd);
+      const uint32_t src = lane_s + uint32_t(rd) * uint32_t(kWarpTrip * 16);
       double2 v[kFpUnroll];
       if (j < ntrips) {
 #pragma unroll
-        for (int u = 0; u < kFpUnroll; ++u) v[u] = ringw[rd * kWarpTrip + u * 32 + lane];
+        for (int u = 0; u < kFpUnroll; ++u) v[u] = lds2(src + uint32_t(u) * 512u);
       } else {
 #pragma unroll
-        for (int u = 0; u < kFpUnroll; ++u)
-          v[u] = (u * 32 + lane < rem) ? ringw[rd * kWarpTrip + u * 32 + lane] : make_double2(0.0, 0.0);
+        for (int u = 0; u < kFpUnroll; ++u) v[u] = (u * 32 + lane < rem) ? lds2(src + uint32_t(u) * 512u) : make_double2(0.0, 0.0);
       }
       __syncwarp();                              // every lane has its data: the slot may be re-armed next trip
-      double t1a = 0.0, t1b = 0.0, q2a = 0.0, q2b = 0.0;
-      if (SUM_ONLY) trip_sum_only(v, rho_new, t1a, t1b);
-      else trip_fast<VARIANT>(v, rho_new, rho_old, t1a, t1b, q2a, q2b);
-      if (finite_f64(t1a + t1b) && finite_f64(q2a + q2b)) {
-        s1a += t1a;
-        s1b += t1b;
-        q2sa += q2a;
-        q2sb += q2b;
-      } else {   // rare: rho = inf / 0 or e at the edge of the exponent range -> IEEE path for this trip
-#pragma unroll 1
-        for (int u = 0; u < kFpUnroll; ++u) {
-          const int64_t i = lo + j * kWarpTrip + u * 32 + lane;
-          if (i < hi) {
-            const double2 w = ld_e2(ev + i);
-            double pn, d;
-            post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
-            s1a += pn;
-            s2a = fma(d, d, s2a);
-            post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
-            s1b += pn;
-            s2b = fma(d, d, s2b);
-          }
-        }
-      }
+      if (SUM_ONLY) trip_sum_only(v, rho_new, s1a, s1b);
+      else trip_fast<VARIANT>(v, rho_new, rho_old, s1a, s1b, q2sa, q2sb);
       rd = (rd + 1 == kFpRingDepth) ? 0 : rd + 1;
       wr = (wr + 1 == kFpRingDepth) ? 0 : wr + 1;
+    }
+    if (!(finite_f64(s1a + s1b) && finite_f64(q2sa + q2sb))) {
+      // rare: rho = inf / 0 or an e at the edge of the exponent range made the fast reciprocal produce inf / NaN somewhere in
+      // this lane's share of the segment -> that share again with the IEEE divisions (exact (pi' - pi)^2 sums)
+      s1a = s1b = q2sa = q2sb = 0.0;
+#pragma unroll 1
+      for (int64_t i = lo + lane; i < hi; i += 32) {
+        const double2 w = ld_e2(ev + i);
+        double pn, d;
+        post_pair_f64<VARIANT>(w.x, rho_new, rho_old, pn, d);
+        s1a += pn;
+        s2a = fma(d, d, s2a);
+        post_pair_f64<VARIANT>(w.y, rho_new, rho_old, pn, d);
+        s1b += pn;
+        s2b = fma(d, d, s2b);
+      }
     }
     // every slot has been read (the __syncwarp of the last trip): arm the next pass's first trips now
     ec.armed = 0;
