@@ -18,6 +18,12 @@
 // `dist` set to every peer's inbox over NVLink) -> all blocks poll their own window (which is the grid barrier)
 // and add the `world` slots in rank order, so every block of every rank sees identical totals and takes the
 // same stop decision.
+//
+// How the later passes get e[] (fp_cache_slots): up to 2^22 samples per GPU the head of the vector stays in shared
+// memory and the rest comes from L2 with per-thread loads; above that every warp streams its own contiguous segment
+// through a private ring of bulk copies (the TMA engine runs ahead of the arithmetic; each pass arms the next pass's
+// first copies before the grid reduction; the head of an HBM-sized vector is kept in L2 by cache hints).
+// RLVI_FP_TRACE=1 prints the per-round timeline of a call (profiles/r02_fixed_point_trace.txt).
 #include <math.h>
 #include <stdlib.h>
 
